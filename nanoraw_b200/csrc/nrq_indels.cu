@@ -1,0 +1,186 @@
+// K0 -- get_all_indels (nanoraw/resquiggle.py:142-201) for a batch of reads.
+//
+// One warp per read walks the two alignment rows 32 columns at a time; gap runs are found
+// with ballots, read-base coordinates with popcount prefix sums.  Two launches: a counting
+// pass (also yields Bg/Br and validates the alignment) and, after an exclusive scan of the
+// counts, a fill pass that writes one (start, end, diff, diff_prefix) int4 per indel.
+#include "nrq_common.cuh"
+
+namespace nrq {
+
+constexpr int kWarpsPerCta = 8;
+
+struct ColMasks {
+  unsigned mr, mg, valid;
+};
+
+__device__ __forceinline__ ColMasks load_cols(const uint8_t* __restrict__ ra,
+                                              const uint8_t* __restrict__ ga, int base, int n) {
+  int c = base + (int)lane_id();
+  bool ok = c < n;
+  bool rg = ok && ra[c] == NRQ_GAP;
+  bool gg = ok && ga[c] == NRQ_GAP;
+  ColMasks m;
+  m.mr = __ballot_sync(0xffffffffu, rg);
+  m.mg = __ballot_sync(0xffffffffu, gg);
+  m.valid = __ballot_sync(0xffffffffu, ok);
+  return m;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_align_count(nrq_batch b, int32_t* __restrict__ status, int32_t* __restrict__ n_indels,
+              int32_t* __restrict__ n_bases) {
+  int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (r >= b.n_reads) return;
+  int64_t a0 = b.align_off[r];
+  int n = (int)(b.align_off[r + 1] - a0);
+  const uint8_t* ra = b.read_align + a0;
+  const uint8_t* ga = b.genome_align + a0;
+  unsigned carry_r = 0, carry_g = 0;
+  int runs = 0, gbases = 0, rbases = 0, bad = 0;
+  for (int base = 0; base < n; base += 32) {
+    ColMasks m = load_cols(ra, ga, base, n);
+    unsigned sr = m.mr & ~((m.mr << 1) | carry_r);
+    unsigned sg = m.mg & ~((m.mg << 1) | carry_g);
+    runs += __popc(sr) + __popc(sg);
+    gbases += __popc(~m.mg & m.valid);
+    rbases += __popc(~m.mr & m.valid);
+    bad |= (m.mr & m.mg) != 0;
+    if (base == 0) bad |= ((m.mr | m.mg) & 1u) != 0;            // must start on a match column
+    if (base + 32 >= n) bad |= (((m.mr | m.mg) >> ((n - 1 - base) & 31)) & 1u) != 0;  // and end on one
+    carry_r = m.mr >> 31;
+    carry_g = m.mg >> 31;
+  }
+  if (lane_id() == 0) {
+    int n_starts = (int)(b.starts_off[r + 1] - b.starts_off[r]);
+    int st = NRQ_ST_OK;
+    if (n <= 0 || n_starts < 2) st = NRQ_ST_BAD_INPUT;
+    else if (bad) st = NRQ_ST_BAD_ALIGNMENT;
+    else if (rbases + 1 != n_starts) st = NRQ_ST_BAD_INPUT;
+    n_indels[r] = (st == NRQ_ST_OK) ? runs : 0;
+    n_bases[r] = gbases;
+    status[r] = st;
+  }
+}
+
+// exclusive scan of int32 counts into int64 offsets; one CTA (R is at most a few million)
+__global__ void __launch_bounds__(1024) k_scan_counts(const int32_t* __restrict__ cnt, int n,
+                                                     int64_t* __restrict__ off) {
+  __shared__ long long part[1024];
+  int t = threadIdx.x;
+  int per = (n + 1023) / 1024;
+  int lo = t * per, hi = min(n, lo + per);
+  long long s = 0;
+  for (int i = lo; i < hi; ++i) s += cnt[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < 1024; d <<= 1) {
+    long long v = (t >= d) ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  long long run = part[t] - s;
+  for (int i = lo; i < hi; ++i) {
+    off[i] = run;
+    run += cnt[i];
+  }
+  if (t == 1023) off[n] = part[1023];
+}
+
+__device__ __forceinline__ int pymod(int a, int n) {
+  int m = a % n;
+  return m < 0 ? m + n : m;
+}
+
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __restrict__ indel_off,
+             int4* __restrict__ indels, int64_t indel_capacity, uint8_t* __restrict__ ev_base,
+             int32_t* __restrict__ status_out) {
+  int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
+  const unsigned lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
+  int64_t a0 = b.align_off[r];
+  int n = (int)(b.align_off[r + 1] - a0);
+  const uint8_t* ra = b.read_align + a0;
+  const uint8_t* ga = b.genome_align + a0;
+  int4* out = indels + indel_off[r];
+  int n_ind = (int)(indel_off[r + 1] - indel_off[r]);
+  if (indel_off[r + 1] > indel_capacity) {  // caller's indel buffer is too small for this read
+    if (lane == 0) status_out[r] = NRQ_ST_WORKSPACE;
+    return;
+  }
+  uint8_t* bases = ev_base ? ev_base + a0 : nullptr;  // align_seq: genome row without gaps (resquiggle.py:384)
+
+  // pass 1: (run start column, run end column, read bases before the run, gap-in-read?)
+  unsigned carry_r = 0, carry_g = 0;
+  int idx_base = 0, rbase = 0, gbase = 0;
+  for (int base = 0; base < n; base += 32) {
+    ColMasks m = load_cols(ra, ga, base, n);
+    if (bases) {
+      unsigned gm = ~m.mg & m.valid;
+      if ((gm >> lane) & 1u) bases[gbase + __popc(gm & lt)] = ga[base + (int)lane];
+      gbase += __popc(gm);
+    }
+    unsigned prev_r = (m.mr << 1) | carry_r, prev_g = (m.mg << 1) | carry_g;
+    unsigned sr = m.mr & ~prev_r, sg = m.mg & ~prev_g;
+    unsigned er = ~m.mr & prev_r & m.valid, eg = ~m.mg & prev_g & m.valid;
+    unsigned sany = sr | sg;
+    int before = idx_base + __popc(sany & lt);
+    int c = base + (int)lane;
+    if ((sany >> lane) & 1u) {
+      out[before].x = c;
+      out[before].z = rbase + __popc(~m.mr & m.valid & lt);
+      out[before].w = (int)((sr >> lane) & 1u);
+    }
+    if (((er | eg) >> lane) & 1u) out[before - 1].y = c;
+    idx_base += __popc(sany);
+    rbase += __popc(~m.mr & m.valid);
+    carry_r = m.mr >> 31;
+    carry_g = m.mg >> 31;
+  }
+  if (n_ind == 0) return;
+  __syncwarp();
+
+  // pass 2: ambiguity extension (resquiggle.py:187-195) and read coordinates, 32 indels at a time
+  int prev_end_carry = 0;  // end column of the indel before this chunk
+  int dpre = 0;
+  for (int base = 0; base < n_ind; base += 32) {
+    int k = base + (int)lane;
+    bool ok = k < n_ind;
+    int4 me = ok ? out[k] : make_int4(0, 0, 0, 0);
+    int up_e = __shfl_up_sync(0xffffffffu, me.y, 1);
+    int prev_end = (lane == 0) ? prev_end_carry : up_e;
+    int next_start = n;
+    if (ok && k + 1 < n_ind) next_start = out[k + 1].x;
+    int last_e = __shfl_sync(0xffffffffu, me.y, 31);
+    __syncwarp();
+    int start = 0, end = 0, diff = 0;
+    if (ok) {
+      int s = me.x, e = me.y, crl = me.z, ins = me.w;
+      int len = e - s;
+      const uint8_t* seq = (ins ? ga : ra) + s;  // :160-164
+      int n_before = s - prev_end, n_after = next_start - e;
+      int d = 0;
+      while (d < n_after - 1 && seq[d % len] == ga[e + d]) ++d;          // :188-190
+      int u = -1;
+      while (-u <= n_before - 1 && seq[pymod(u, len)] == ga[s + u]) --u;  // :191-193
+      start = crl + u;
+      end = (ins ? crl + 1 : crl + len + 1) + d;                          // :178-179
+      diff = ins ? len : -len;                                             // :180
+    }
+    // exclusive prefix of diff
+    int inc = diff;
+    for (int o = 1; o < 32; o <<= 1) {
+      int v = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((int)lane >= o) inc += v;
+    }
+    if (ok) out[k] = make_int4(start, end, diff, dpre + inc - diff);
+    dpre += __shfl_sync(0xffffffffu, inc, 31);
+    prev_end_carry = last_e;
+    __syncwarp();
+  }
+}
+
+}  // namespace nrq

@@ -1,0 +1,283 @@
+// K2 -- get_indel_groups + splice (nanoraw/resquiggle.py:203-316, 362-387).
+//
+// A read is a sequential, data-dependent state machine over its indels (a failed change-point
+// search grows the region, which may swallow finished groups), so parallelism is across reads:
+// one warp owns one read at a time and pulls the next from a global work counter.  Inside a
+// candidate region the warp cooperates: lanes normalise the region's samples into shared memory,
+// lane 0 runs the strictly sequential float64 cumulative sum (the reference restarts np.cumsum at
+// every candidate region, so every rounding step has to be replayed in order), all lanes form the
+// running differences, and the change-points are chosen by repeated masked arg-max under the
+// total order (value desc, index desc) == greedy over argsort(kind='stable')[::-1].
+//
+// Finished change-points are written straight into their final new_segs slots: an untouched
+// boundary starts[j] lands at j + D, D = sum of indel diffs of the groups before it, so a group
+// (start, stop, K) owns new_segs[start + D + 1 .. start + D + K].
+#include "nrq_common.cuh"
+
+namespace nrq {
+
+constexpr int kSegWarps = 8;
+constexpr int kRegionCap = 512;  // region samples held in shared memory per warp (p99 of real regions ~200)
+constexpr unsigned kFull = 0xffffffffu;
+
+struct SegCtx {
+  const int32_t* t;   // starts_rel_to_read
+  int last;           // Br (largest index into t)
+  const int16_t* sig;
+  NormCoef coef;
+  const int4* ind;    // (start, end, diff, diff_prefix)
+  int n_ind;
+  int4* groups;       // finished groups: (start, stop, first indel, max indel end)
+  int ng;
+  int32_t* out;       // new_segs
+  int m;              // min_seg_len
+  int limit;          // cpts limit or < 0
+  double* buf_sm;
+  double* buf_big;
+  int big_cap;
+};
+
+// extend_group, resquiggle.py:203-216
+__device__ __forceinline__ int extend_group(const SegCtx& c, int lo, int hi, int maxend,
+                                            int& start, int& stop, int& K) {
+  int4 a = c.ind[lo], z = c.ind[hi];
+  start = a.x;
+  stop = maxend;
+  if (start < 0 || stop > c.last) return NRQ_ST_BAD_ALIGNMENT;
+  K = (z.w + z.z - a.w) + stop - start - 1;
+  while (c.t[stop] - c.t[start] < (K + 2) * c.m) {
+    if (start == 0 && stop == c.last) return NRQ_ST_UNSATISFIABLE;
+    K += (start > 0) + (stop < c.last);
+    start = max(0, start - 1);
+    stop = min(c.last, stop + 1);
+  }
+  return NRQ_ST_OK;
+}
+
+// the merge loop shared by extend_and_join (:220-225) and extend_for_cpts (:267-272)
+__device__ __forceinline__ int swallow_previous(SegCtx& c, int& lo, int hi, int& maxend,
+                                                int& start, int& stop, int& K) {
+  while (c.ng > 0) {
+    int4 prev = c.groups[c.ng - 1];
+    if (start > prev.y) break;
+    --c.ng;
+    lo = prev.z;
+    maxend = max(maxend, prev.w);
+    int st = extend_group(c, lo, hi, maxend, start, stop, K);
+    if (st != NRQ_ST_OK) return st;
+  }
+  return NRQ_ST_OK;
+}
+
+// get_cpts, resquiggle.py:227-255.  1: change-points written to out[outpos..outpos+K); 0: None;
+// < 0: -status.
+__device__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos) {
+  if (c.limit >= 0 && K > c.limit) return -NRQ_ST_CPTS_LIMIT;
+  const unsigned lane = lane_id();
+  const int m = c.m;
+  const int t0 = c.t[start];
+  const int n = c.t[stop] - t0;
+  const int nrd = n - 2 * m + 1;  // len(running_diffs)
+  if (nrd <= 0) return 0;
+  double* buf = c.buf_sm;
+  if (n > kRegionCap) {
+    if (n > c.big_cap) return -NRQ_ST_REGION_TOO_LARGE;
+    buf = c.buf_big;
+  }
+  // x = normalised, clipped signal of the region; buf[j+1] = x[j], buf[0] = 0  (:237-239)
+  const int16_t* s = c.sig + t0;
+  for (int j = lane; j < n; j += 32) buf[j + 1] = norm_value((int)s[j], c.coef);
+  if (lane == 0) buf[0] = 0.0;
+  __syncwarp();
+  if (lane == 0) {  // np.cumsum: strictly left to right
+    double acc = 0.0;
+    int j = 1;
+    for (; j + 3 <= n; j += 4) {
+      double x0 = buf[j], x1 = buf[j + 1], x2 = buf[j + 2], x3 = buf[j + 3];
+      acc = __dadd_rn(acc, x0); buf[j] = acc;
+      acc = __dadd_rn(acc, x1); buf[j + 1] = acc;
+      acc = __dadd_rn(acc, x2); buf[j + 2] = acc;
+      acc = __dadd_rn(acc, x3); buf[j + 3] = acc;
+    }
+    for (; j <= n; ++j) { acc = __dadd_rn(acc, buf[j]); buf[j] = acc; }
+  }
+  __syncwarp();
+  // running_diffs[i] = |2 cs[i+m] - cs[i] - cs[i+2m]| (:241-243), stored in place as an ordered
+  // key: bits + 2 (0 = blacklisted, 1 = picked)
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(buf);
+  for (int base = 0; base < nrd; base += 32) {
+    int i = base + (int)lane;
+    unsigned long long k = 0;
+    if (i < nrd) {
+      double a = buf[i], bq = buf[i + m], cq = buf[i + 2 * m];
+      double rd = fabs(__dsub_rn(__dsub_rn(__dmul_rn(2.0, bq), a), cq));
+      k = (unsigned long long)__double_as_longlong(rd) + 2ull;
+    }
+    __syncwarp();
+    if (i < nrd) key[i] = k;
+  }
+  __syncwarp();
+  // greedy selection (:244-254)
+  for (int round = 0; round < K; ++round) {
+    unsigned long long best = 0;
+    int bi = -1;
+    for (int i = lane; i < nrd; i += 32) {
+      unsigned long long k = key[i];
+      if (k >= 2ull && k >= best) { best = k; bi = i; }
+    }
+    unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+    unsigned mh = __reduce_max_sync(kFull, hi);
+    bool c1 = hi == mh;
+    unsigned ml = __reduce_max_sync(kFull, c1 ? lo : 0u);
+    bool c2 = c1 && lo == ml;
+    unsigned mi = __reduce_max_sync(kFull, c2 ? (unsigned)(bi + 1) : 0u);
+    if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
+    int p = (int)mi - 1;
+    if ((int)lane < 2 * m) {
+      int q = p - m + 1 + (int)lane;  // blacklist p-m+1 .. p+m (:249-250)
+      if (q >= 0 && q < nrd) {
+        if (q == p) key[q] = 1ull;
+        else if (key[q] != 1ull) key[q] = 0ull;
+      }
+    }
+    __syncwarp();
+  }
+  // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
+  int cnt = 0;
+  for (int base = 0; base < nrd; base += 32) {
+    int i = base + (int)lane;
+    bool f = i < nrd && key[i] == 1ull;
+    unsigned bal = __ballot_sync(kFull, f);
+    if (f) c.out[outpos + cnt + __popc(bal & ((1u << lane) - 1u))] = t0 + i + m;
+    cnt += __popc(bal);
+  }
+  return 1;
+}
+
+// extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
+__device__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
+  int K;
+  int st = extend_group(c, lo, hi, maxend, start, stop, K);
+  if (st != NRQ_ST_OK) return st;
+  st = swallow_previous(c, lo, hi, maxend, start, stop, K);
+  if (st != NRQ_ST_OK) return st;
+  for (;;) {
+    int res = get_cpts(c, start, stop, K, start + c.ind[lo].w + 1);
+    if (res > 0) return NRQ_ST_OK;
+    if (res < 0) return -res;
+    if (start == 0 && stop == c.last) return NRQ_ST_UNSATISFIABLE;
+    K += (start > 0) + (stop < c.last);
+    start = max(0, start - 1);
+    stop = min(c.last, stop + 1);
+    st = swallow_previous(c, lo, hi, maxend, start, stop, K);
+    if (st != NRQ_ST_OK) return st;
+  }
+}
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm) {
+  const unsigned lane = lane_id();
+  const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
+  int dtotal = 0;
+  if (c.n_ind > 0) {
+    int lo = 0, hi = 0, maxend = c.ind[0].y;
+    int start, stop;
+    for (int k = 1; k < c.n_ind; ++k) {
+      if (timeout_ns > 0 && global_ns() - t_begin > timeout_ns) return NRQ_ST_TIMEOUT;  // :288-289
+      int4 nxt = c.ind[k];
+      if (maxend >= nxt.x) {  // :291-292
+        hi = k;
+        maxend = max(maxend, nxt.y);
+        continue;
+      }
+      int st = close_group(c, lo, hi, maxend, start, stop);
+      if (st != NRQ_ST_OK) return st;
+      if (stop >= nxt.x) {  // :299-300
+        hi = k;
+        maxend = max(maxend, nxt.y);
+      } else {  // :302-304
+        if (lane == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
+        __syncwarp();
+        ++c.ng;
+        lo = hi = k;
+        maxend = nxt.y;
+      }
+    }
+    int st = close_group(c, lo, hi, maxend, start, stop);  // :307-314
+    if (st != NRQ_ST_OK) return st;
+    if (lane == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
+    __syncwarp();
+    ++c.ng;
+    int4 z = c.ind[c.n_ind - 1];
+    dtotal = z.w + z.z;
+  }
+  // splice (:362-372): untouched boundaries between groups
+  int prev_stop = 0;
+  for (int g = 0; g <= c.ng; ++g) {
+    int upto, d;
+    if (g < c.ng) {
+      int4 grp = c.groups[g];
+      upto = grp.x;
+      d = c.ind[grp.z].w;
+      for (int j = prev_stop + (int)lane; j <= upto; j += 32) c.out[j + d] = c.t[j];
+      prev_stop = grp.y;
+    } else {
+      for (int j = prev_stop + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = c.t[j];
+    }
+  }
+  __syncwarp();
+  // validation (:373-387)
+  const int total = c.last + 1 + dtotal;
+  int zero_len = 0;
+  for (int i = lane; i + 1 < total; i += 32) zero_len |= (c.out[i + 1] - c.out[i] < 1);
+  zero_len = __any_sync(kFull, zero_len);
+  if (zero_len) return NRQ_ST_ZERO_LEN;
+  if (c.out[0] < 0) return NRQ_ST_NEG_START;
+  if (c.out[total - 1] > n_norm) return NRQ_ST_PAST_END;
+  if (total != n_bases + 1) return NRQ_ST_SEQ_MISMATCH;
+  return NRQ_ST_OK;
+}
+
+__global__ void __launch_bounds__(kSegWarps * 32)
+k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int64_t* __restrict__ indel_off,
+            const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
+            double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
+            int32_t* __restrict__ new_segs) {
+  __shared__ double region[kSegWarps][kRegionCap + 1];
+  const int warp = threadIdx.x >> 5;
+  const unsigned lane = lane_id();
+  const int gwarp = blockIdx.x * kSegWarps + warp;
+  for (;;) {
+    int r = 0;
+    if (lane == 0) r = atomicAdd(work_counter, 1);
+    r = __shfl_sync(kFull, r, 0);
+    if (r >= b.n_reads) break;
+    if (status[r] != NRQ_ST_OK) continue;
+    ReadGeom g = read_geom(b, r);
+    SegCtx c;
+    c.t = g.starts;
+    c.last = g.n_starts - 1;
+    c.sig = g.sig;
+    c.coef = load_coef(sv, r);
+    c.ind = indels + indel_off[r];
+    c.n_ind = (int)(indel_off[r + 1] - indel_off[r]);
+    c.groups = group_scratch + indel_off[r];
+    c.ng = 0;
+    c.out = new_segs + b.align_off[r] + r;
+    c.m = p.min_seg_len;
+    c.limit = p.num_cpts_limit;
+    c.buf_sm = region[warp];
+    c.big_cap = p.big_region_cap;
+    c.buf_big = big_scratch + (size_t)gwarp * (size_t)(p.big_region_cap + 1);
+    int st = resegment_read(c, p.timeout_ns, n_bases[r], g.n_norm);
+    if (lane == 0 && st != NRQ_ST_OK) status[r] = st;
+    __syncwarp();
+  }
+}
+
+}  // namespace nrq

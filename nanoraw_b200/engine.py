@@ -1,0 +1,276 @@
+"""Device pipeline: ReadBatch -> libnrq kernels -> per-read results.
+
+PyTorch owns device memory and the CUDA stream; every computation is a libnrq kernel
+reached through the C ABI in include/nrq.h.  No CPU fallback exists: constructing an
+engine without a CUDA device or without libnrq.so raises.
+"""
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from .batch import ReadBatch
+
+EVENT_DTYPE = np.dtype([('norm_mean', '<f8'), ('norm_stdev', '<f8'),
+                        ('start', '<u4'), ('length', '<u4'), ('base', 'S1')])
+
+
+@dataclass
+class ResquiggleParams:
+    """Batch-wide options = the CLI-level arguments of resquiggle_read (resquiggle.py:318-323)."""
+    norm_type: str = 'median'            # 'median' | 'none' | 'pA_raw' | 'pA' | 'given'
+    outlier_thresh: Optional[float] = 5  # None disables clipping (resquiggle.py:1159-1160)
+    compute_sd: bool = True
+    num_cpts_limit: Optional[int] = None
+    timeout: Optional[float] = None      # seconds, measured on the device clock
+    min_event_obs: int = 4
+    given_limits: bool = False
+    big_region_cap: int = 16384
+    debug_flags: int = 0
+
+    def to_c(self):
+        p = _lib.NrqParams()
+        p.norm_type = _lib.NORM_MEDIAN if self.norm_type == 'median' else _lib.NORM_GIVEN
+        p.use_outlier = 0 if self.outlier_thresh is None else 1
+        p.outlier_thresh = 0.0 if self.outlier_thresh is None else float(self.outlier_thresh)
+        p.given_limits = int(self.given_limits)
+        p.compute_sd = int(self.compute_sd)
+        p.num_cpts_limit = -1 if self.num_cpts_limit is None else int(self.num_cpts_limit)
+        p.min_seg_len = int(self.min_event_obs)
+        p.timeout_ns = 0 if self.timeout is None else int(self.timeout * 1e9)
+        p.big_region_cap = int(self.big_region_cap)
+        p.debug_flags = int(self.debug_flags)
+        return p
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DeviceBatch(object):
+    """A ReadBatch resident in HBM (torch tensors) plus the nrq_batch struct pointing at it."""
+
+    def __init__(self, batch: ReadBatch, device, non_blocking=False, pin=False):
+        import torch
+        self.n_reads = batch.n_reads
+        self.total_align = batch.total_align
+        self.device = device
+        self.host = batch
+        self.t = {}
+        for name in ReadBatch.FIELDS + ('scale_values_in',):
+            arr = getattr(batch, name)
+            if arr is None:
+                self.t[name] = None
+                continue
+            ht = torch.from_numpy(np.ascontiguousarray(arr))
+            if pin:
+                ht = ht.pin_memory()
+            self.t[name] = ht.to(device, non_blocking=non_blocking)
+        self.c = self._struct()
+
+    def _struct(self):
+        b = _lib.NrqBatch()
+        b.n_reads = self.n_reads
+        for name in ReadBatch.FIELDS + ('scale_values_in',):
+            setattr(b, name, _ptr(self.t[name]))
+        return b
+
+    def device_bytes(self):
+        return sum(t.numel() * t.element_size() for t in self.t.values() if t is not None)
+
+
+class DeviceResults(object):
+    """Output arrays of nrq_resquiggle_batch in HBM."""
+
+    def __init__(self, n_reads, total_align, device):
+        import torch
+        R, A = n_reads, total_align
+        mk = lambda n, dt: torch.empty(max(int(n), 1), dtype=dt, device=device)
+        self.status = mk(R, torch.int32)
+        self.n_bases = mk(R, torch.int32)
+        self.n_indels = mk(R, torch.int32)
+        self.scale_values = mk(4 * R, torch.float64)
+        self.new_segs = mk(A + R, torch.int32)
+        self.norm_mean = mk(A, torch.float64)
+        self.norm_stdev = mk(A, torch.float64)
+        self.ev_start = mk(A, torch.int32)    # bit pattern of uint32
+        self.ev_length = mk(A, torch.int32)
+        self.ev_base = mk(A, torch.uint8)
+        c = _lib.NrqResults()
+        for name, _ in _lib.NrqResults._fields_:
+            setattr(c, name, _ptr(getattr(self, name)))
+        self.c = c
+
+    NAMES = tuple(n for n, _ in _lib.NrqResults._fields_)
+
+    def device_bytes(self):
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size() for n in self.NAMES)
+
+
+class HostResults(object):
+    """Results of a batch on the host, with per-read accessors shaped like the reference's
+    outputs (new_segs: resquiggle.py:372; event table: resquiggle.py:66-70)."""
+
+    def __init__(self, align_off, arrays):
+        self.align_off = np.asarray(align_off)
+        for k, v in arrays.items():
+            setattr(self, k, v)
+        self.scale_values = self.scale_values.reshape(-1, 4)
+
+    @property
+    def n_reads(self):
+        return len(self.status)
+
+    def ok(self, r):
+        return int(self.status[r]) == _lib.ST_OK
+
+    def error(self, r):
+        return _lib.status_message(self.status[r])
+
+    def new_segs_of(self, r):
+        o = int(self.align_off[r]) + r
+        return self.new_segs[o:o + int(self.n_bases[r]) + 1].astype(np.int64)
+
+    def scale_values_of(self, r):
+        """(shift, scale, lower_lim, upper_lim); None where the reference has None."""
+        return tuple(None if np.isnan(v) else float(v) for v in self.scale_values[r])
+
+    def events_of(self, r):
+        o, n = int(self.align_off[r]), int(self.n_bases[r])
+        ev = np.empty(n, dtype=EVENT_DTYPE)
+        ev['norm_mean'] = self.norm_mean[o:o + n]
+        ev['norm_stdev'] = self.norm_stdev[o:o + n]
+        ev['start'] = self.ev_start[o:o + n]
+        ev['length'] = self.ev_length[o:o + n]
+        ev['base'] = self.ev_base[o:o + n].view('S1')
+        return ev
+
+
+class ResquiggleEngine(object):
+    """Runs the a1..a7 hot path for batches of reads on one GPU."""
+
+    def __init__(self, device=None):
+        import torch
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.NrqError('no CUDA device: the re-squiggle path has no CPU fallback')
+        self.torch = torch
+        self.device = torch.device('cuda', torch.cuda.current_device() if device is None else device)
+        self._ws = None
+
+    # ---- plumbing
+    def _stream(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    def workspace(self, n_reads, total_align, params_c, min_bytes=0):
+        need = max(int(self.lib.nrq_workspace_bytes(n_reads, total_align, C.byref(params_c))), min_bytes)
+        if need < 0:
+            raise _lib.NrqError(self.lib.nrq_last_error().decode())
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = None
+            self._ws = self.torch.empty(need, dtype=self.torch.uint8, device=self.device)
+        return self._ws
+
+    def upload(self, batch, pin=False):
+        with self.torch.cuda.device(self.device):
+            return DeviceBatch(batch, self.device, pin=pin)
+
+    def alloc_results(self, dbatch):
+        return DeviceResults(dbatch.n_reads, dbatch.total_align, self.device)
+
+    # ---- the whole path, device resident (kernel-only timing uses this)
+    def run_device(self, dbatch, params, out=None, workspace=None):
+        pc = params.to_c() if isinstance(params, ResquiggleParams) else params
+        with self.torch.cuda.device(self.device):
+            out = out or self.alloc_results(dbatch)
+            ws = workspace if workspace is not None else self.workspace(
+                dbatch.n_reads, dbatch.total_align, pc)
+            rc = self.lib.nrq_resquiggle_batch(
+                C.byref(dbatch.c), C.byref(pc), C.byref(out.c), _ptr(ws), ws.numel(), self._stream())
+        _lib.check(rc, 'nrq_resquiggle_batch')
+        return out
+
+    def download(self, dbatch, out):
+        arrays = {}
+        for name in DeviceResults.NAMES:
+            a = getattr(out, name).cpu().numpy()
+            if name in ('ev_start', 'ev_length'):
+                a = a.view(np.uint32)
+            arrays[name] = a
+        R = dbatch.n_reads
+        for name in ('status', 'n_bases', 'n_indels'):
+            arrays[name] = arrays[name][:R]
+        arrays['scale_values'] = arrays['scale_values'][:4 * R]
+        return HostResults(dbatch.host.align_off, arrays)
+
+    def run(self, batch, params):
+        """Host arrays in, host arrays out.  Reads the indel workspace could not hold are
+        re-run once with a workspace sized for the worst case."""
+        db = self.upload(batch)
+        pc = params.to_c()
+        out = self.run_device(db, pc)
+        res = self.download(db, out)
+        if (res.status == _lib.ST_WORKSPACE).any():
+            ws = self.workspace(db.n_reads, db.total_align, pc,
+                                min_bytes=32 * (db.total_align + db.n_reads) + (1 << 20) +
+                                int(self.lib.nrq_workspace_bytes(db.n_reads, 0, C.byref(pc))))
+            out = self.run_device(db, pc, out=out, workspace=ws)
+            res = self.download(db, out)
+        return res
+
+    # ---- single stages (tests, normalize_raw_signal / get_indel_groups call surfaces)
+    def find_indels(self, dbatch):
+        """-> (status, n_indels, n_bases, indel_off, indels[I,4]) on the host."""
+        t = self.torch
+        R = dbatch.n_reads
+        with t.cuda.device(self.device):
+            status = t.empty(R, dtype=t.int32, device=self.device)
+            n_ind = t.empty(R, dtype=t.int32, device=self.device)
+            n_bases = t.empty(R, dtype=t.int32, device=self.device)
+            off = t.empty(R + 1, dtype=t.int64, device=self.device)
+            rc = self.lib.nrq_find_indels(C.byref(dbatch.c), _ptr(status), _ptr(n_ind), _ptr(n_bases),
+                                          _ptr(off), C.c_void_p(0), 0, C.c_void_p(0), self._stream())
+            _lib.check(rc, 'nrq_find_indels')
+            total = int(off[-1].item())
+            indels = t.empty(4 * max(total, 1), dtype=t.int32, device=self.device)
+            bases = t.empty(max(dbatch.total_align, 1), dtype=t.uint8, device=self.device)
+            rc = self.lib.nrq_find_indels(C.byref(dbatch.c), _ptr(status), _ptr(n_ind), _ptr(n_bases),
+                                          _ptr(off), _ptr(indels), total, _ptr(bases), self._stream())
+            _lib.check(rc, 'nrq_find_indels')
+        return (status.cpu().numpy(), n_ind.cpu().numpy(), n_bases.cpu().numpy(), off.cpu().numpy(),
+                indels.cpu().numpy()[:4 * total].reshape(-1, 4), bases.cpu().numpy())
+
+    def norm_stats(self, dbatch, params, status=None):
+        t = self.torch
+        R = dbatch.n_reads
+        pc = params.to_c()
+        with t.cuda.device(self.device):
+            if status is None:
+                status = t.zeros(R, dtype=t.int32, device=self.device)
+            sv = t.empty(4 * R, dtype=t.float64, device=self.device)
+            rc = self.lib.nrq_norm_stats(C.byref(dbatch.c), C.byref(pc), _ptr(status), _ptr(sv), self._stream())
+            _lib.check(rc, 'nrq_norm_stats')
+        return status, sv
+
+    def normalize_signal(self, dbatch, params):
+        """-> (status, scale_values[R,4], [float64 normalised signal per read]) on the host."""
+        t = self.torch
+        status, sv = self.norm_stats(dbatch, params)
+        n_samp = dbatch.host.n_samples
+        off = np.zeros(dbatch.n_reads + 1, dtype=np.int64)
+        np.cumsum(n_samp, out=off[1:])
+        with t.cuda.device(self.device):
+            d_off = t.from_numpy(off).to(self.device)
+            sig = t.full((max(int(off[-1]), 1),), float('nan'), dtype=t.float64, device=self.device)
+            rc = self.lib.nrq_normalize_signal(C.byref(dbatch.c), _ptr(sv), _ptr(status), _ptr(d_off),
+                                               _ptr(sig), self._stream())
+            _lib.check(rc, 'nrq_normalize_signal')
+        st = status.cpu().numpy()
+        svh = sv.cpu().numpy().reshape(-1, 4)
+        h = sig.cpu().numpy()
+        raw_len = np.diff(dbatch.host.raw_off) - dbatch.host.read_start
+        sigs = [h[off[r]:off[r] + min(int(n_samp[r]), max(int(raw_len[r]), 0))]
+                for r in range(dbatch.n_reads)]
+        return st, svh, sigs

@@ -1,0 +1,225 @@
+"""Parity of the CUDA path (through the C ABI) against the reference-pinned goldens and the
+oracle.  Bit-exact: boundaries, scale values, normalised signal; event means / sds are also
+compared exactly (the kernel follows numpy's summation order), with the contract's 1e-9
+tolerance as the documented fallback bar."""
+import numpy as np
+import pytest
+
+from golden_util import load_golden
+from nanoraw_b200 import synth
+from nanoraw_b200.batch import ReadBatch
+from oracle import resquiggle_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+INFO, CASES = load_golden()
+TOL = 1e-9
+
+
+def close(a, b):
+    """abs(a-b) <= 1e-9 * max(1, |a|, |b|), NaN == NaN."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    both_nan = np.isnan(a) & np.isnan(b)
+    lim = TOL * np.maximum(1.0, np.maximum(np.abs(a), np.abs(b)))
+    return bool(np.all(both_nan | (np.abs(a - b) <= lim)))
+
+
+@pytest.fixture(scope='module')
+def engine():
+    from nanoraw_b200.engine import ResquiggleEngine
+    return ResquiggleEngine()
+
+
+def given_scale_values(case):
+    nt = case.params.get('norm_type', 'median')
+    ch = INFO['channel']
+    if nt == 'none':
+        return [0.0, 1.0, np.nan, np.nan]
+    if nt == 'pA_raw':
+        return [-1.0 * np.float64(ch['offset']),
+                np.float64(ch['digitisation']) / np.float64(ch['range']), np.nan, np.nan]
+    return None
+
+
+def groups_by_params():
+    groups = {}
+    for c in CASES:
+        key = (c.params.get('norm_type', 'median'), c.params.get('outlier_thresh', 5),
+               c.params.get('num_cpts_limit'), c.params.get('compute_sd', True))
+        groups.setdefault(key, []).append(c)
+    return groups
+
+
+def run_cases(engine, cases, key, debug_flags=0):
+    from nanoraw_b200.engine import ResquiggleParams
+    norm_type, thresh, limit, sd = key
+    sv_in = None
+    if norm_type != 'median':
+        sv_in = np.array([given_scale_values(c) for c in cases])
+    batch = ReadBatch.from_reads([c.read for c in cases], sv_in)
+    params = ResquiggleParams(norm_type=norm_type, outlier_thresh=thresh, num_cpts_limit=limit,
+                              compute_sd=sd, debug_flags=debug_flags)
+    return engine.run(batch, params)
+
+
+def golden_new_segs(a):
+    return np.concatenate([a['ev_start'], [a['ev_start'][-1] + a['ev_length'][-1]]]).astype(np.int64)
+
+
+def check_case(case, res, r):
+    from nanoraw_b200.errors import error_string
+    a = case.a
+    if case.error:
+        assert error_string(res.status[r]) == case.error, case.name
+        return
+    assert res.ok(r), (case.name, res.error(r))
+    assert np.array_equal(res.scale_values[r], a['scale_values'], equal_nan=True), case.name
+    if 'ev_start' in a:
+        assert np.array_equal(res.new_segs_of(r), golden_new_segs(a)), case.name
+        ev = res.events_of(r)
+        assert np.array_equal(ev['start'], a['ev_start']) and np.array_equal(ev['length'], a['ev_length'])
+        assert np.array_equal(ev['base'], a['ev_base'])
+        assert close(ev['norm_mean'], a['ev_mean']) and close(ev['norm_stdev'], a['ev_sd']), case.name
+        assert np.array_equal(ev['norm_mean'], a['ev_mean']), case.name + ' (mean not bit-exact)'
+        assert np.array_equal(ev['norm_stdev'], a['ev_sd'], equal_nan=True), case.name + ' (sd not bit-exact)'
+    else:
+        # FAST5 write fails in the reference (outlier_threshold=None attr); compare change-points
+        segs = res.new_segs_of(r)
+        assert set(a['cpts'].tolist()) <= set(segs.tolist()), case.name
+        assert len(segs) == int(res.n_bases[r]) + 1
+
+
+def test_golden_whole_path(engine):
+    for key, cases in groups_by_params().items():
+        res = run_cases(engine, cases, key)
+        for r, case in enumerate(cases):
+            check_case(case, res, r)
+
+
+def test_golden_general_order_statistics(engine):
+    """debug bit 0 forces the bisection path of nrq_norm_stats for every read."""
+    for key, cases in groups_by_params().items():
+        res = run_cases(engine, cases, key, debug_flags=1)
+        for r, case in enumerate(cases):
+            check_case(case, res, r)
+
+
+def test_golden_indels(engine):
+    cases = [c for c in CASES if 'indels' in c.a]
+    db = engine.upload(ReadBatch.from_reads([c.read for c in cases]))
+    status, n_ind, n_bases, off, indels, bases = engine.find_indels(db)
+    for r, c in enumerate(cases):
+        assert status[r] == 0
+        mine = indels[off[r]:off[r + 1]]
+        assert np.array_equal(mine[:, :3], c.a['indels']), c.name
+        assert np.array_equal(mine[:, 3], np.concatenate([[0], np.cumsum(c.a['indels'][:, 2])[:-1]])
+                              if len(mine) else mine[:, 3])
+        g = np.frombuffer(c.read.genome_align, dtype=np.uint8)
+        assert n_bases[r] == int((g != ord('-')).sum())
+        a0 = int(db.host.align_off[r])
+        assert np.array_equal(bases[a0:a0 + n_bases[r]], g[g != ord('-')])
+
+
+def test_golden_normalised_signal(engine):
+    from nanoraw_b200.engine import ResquiggleParams
+    for key, cases in groups_by_params().items():
+        cases = [c for c in cases if 'norm_signal' in c.a]
+        if not cases:
+            continue
+        norm_type, thresh, _, _ = key
+        sv_in = None if norm_type == 'median' else np.array([given_scale_values(c) for c in cases])
+        db = engine.upload(ReadBatch.from_reads([c.read for c in cases], sv_in))
+        st, sv, sigs = engine.normalize_signal(
+            db, ResquiggleParams(norm_type=norm_type, outlier_thresh=thresh))
+        for r, c in enumerate(cases):
+            assert np.array_equal(sv[r], c.a['scale_values'], equal_nan=True), c.name
+            assert np.array_equal(sigs[r], c.a['norm_signal']), c.name
+
+
+SEEDED = {
+    'standard_10kb': (synth.SynthConfig(seed_base=41000), 6),
+    'short_4kb': (synth.config_short(42000), 8),
+    'indel_dense': (synth.config_indel_dense(43000), 4),
+    'low_dwell': (synth.SynthConfig(span_mean=3000, span_sd=300, dwell_mean=6.2, seed_base=44000), 6),
+    'long_100kb': (synth.SynthConfig(span_mean=100_000, span_sd=5_000, seed_base=45000), 1),
+}
+
+
+@pytest.mark.parametrize('name', list(SEEDED))
+def test_seeded_reads_against_oracle(engine, name):
+    from nanoraw_b200.engine import ResquiggleParams
+    cfg, n = SEEDED[name]
+    genome = synth.make_genome(1_000_000, seed=9)
+    reads = synth.make_reads(n, cfg, genome=genome)
+    res = engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+    for r, read in enumerate(reads):
+        out = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                                  read.read_align.decode(), read.genome_align.decode())
+        assert res.ok(r), res.error(r)
+        assert res.scale_values_of(r) == tuple(float(v) for v in out['scale_values'])
+        assert np.array_equal(res.new_segs_of(r), out['new_segs'])
+        ev = res.events_of(r)
+        for col in ('start', 'length', 'base'):
+            assert np.array_equal(ev[col], out['events'][col])
+        assert close(ev['norm_mean'], out['events']['norm_mean'])
+        assert close(ev['norm_stdev'], out['events']['norm_stdev'])
+        assert np.array_equal(ev['norm_mean'], out['events']['norm_mean'])
+        assert np.array_equal(ev['norm_stdev'], out['events']['norm_stdev'])
+
+
+def test_unsatisfiable_region_terminates(engine):
+    """mean dwell <= 5 samples/base: the reference loops forever (resquiggle.py:210-215);
+    the device path must stop with NRQ_ST_UNSATISFIABLE like the oracle's guard."""
+    from nanoraw_b200.engine import ResquiggleParams
+    from nanoraw_b200 import _lib
+    cfg = synth.SynthConfig(span_mean=300, span_sd=10, dwell_mean=3.2, dwell_min=2, seed_base=46000)
+    reads = synth.make_reads(4, cfg, genome=synth.make_genome(100_000, seed=9))
+    res = engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+    for r, read in enumerate(reads):
+        try:
+            out = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                                      read.read_align.decode(), read.genome_align.decode())
+        except orc.RegionUnsatisfiable:
+            assert res.status[r] == _lib.ST_UNSATISFIABLE
+        else:
+            assert res.ok(r) and np.array_equal(res.new_segs_of(r), out['new_segs'])
+
+
+def test_host_buffer_entry_point(engine):
+    """nrq_resquiggle_batch_host (host pointers in/out) == the torch-managed route."""
+    import ctypes as C
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.engine import ResquiggleParams
+    reads = synth.make_reads(5, synth.config_short(47000), genome=synth.make_genome(200_000, seed=9))
+    batch = ReadBatch.from_reads(reads)
+    params = ResquiggleParams()
+    want = engine.run(batch, params)
+    lib = _lib.load()
+    R, A = batch.n_reads, batch.total_align
+    hb = _lib.NrqBatch()
+    hb.n_reads = R
+    keep = []
+    for f in ReadBatch.FIELDS:
+        arr = np.ascontiguousarray(getattr(batch, f))
+        keep.append(arr)
+        setattr(hb, f, arr.ctypes.data)
+    outs = {'status': np.zeros(R, np.int32), 'n_bases': np.zeros(R, np.int32),
+            'n_indels': np.zeros(R, np.int32), 'scale_values': np.zeros(4 * R),
+            'new_segs': np.zeros(A + R, np.int32), 'norm_mean': np.zeros(A), 'norm_stdev': np.zeros(A),
+            'ev_start': np.zeros(A, np.uint32), 'ev_length': np.zeros(A, np.uint32),
+            'ev_base': np.zeros(A, np.uint8)}
+    hr = _lib.NrqResults()
+    for k, v in outs.items():
+        setattr(hr, k, v.ctypes.data)
+    h = lib.nrq_create(engine.device.index or 0)
+    assert h
+    pc = params.to_c()
+    _lib.check(lib.nrq_resquiggle_batch_host(h, C.byref(hb), C.byref(pc), C.byref(hr)), 'host batch')
+    lib.nrq_destroy(h)
+    assert np.array_equal(outs['status'], want.status)
+    for r in range(R):
+        o, n = int(batch.align_off[r]), int(want.n_bases[r])
+        assert np.array_equal(outs['new_segs'][o + r:o + r + n + 1], want.new_segs_of(r))
+        assert np.array_equal(outs['norm_mean'][o:o + n], want.norm_mean[o:o + n])
+        assert np.array_equal(outs['norm_stdev'][o:o + n], want.norm_stdev[o:o + n])
