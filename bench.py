@@ -1,0 +1,487 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the genome_resquiggle hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+
+A step is one pass of the whole a1..a7 path (indel scan, median/MAD order statistics,
+re-segmentation, event table) over one batch of synthetic reads.  At N = 1 the workload is
+BASELINE.json configs[1]: 100k synthetic ~10 kb reads resident in HBM.  For N > 1 every rank
+holds its own 100k reads (reads are independent: no collective on the data path; weak scaling).
+
+One JSON line on stdout (rank 0).  `value` is kernel-only samples/s with inputs resident in
+HBM; `e2e` is the same metric through the C-ABI host-buffer call (nrq_resquiggle_batch_host)
+with pinned host inputs/outputs and both copies inside the timed region; `roofline` is the
+dominant kernel's algorithmic bytes / its CUDA-event time against the measured HBM peak;
+`cpu_baseline` is the oracle port timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from nanoraw_b200 import synth  # noqa: E402
+
+METRIC = 'resquiggled raw samples/sec'
+UNIT = 'samples/s'
+STAGES = ('k_align_scan', 'k_norm_stats', 'k_resegment', 'k_event_table')
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_config(name, seed_base):
+    cfg = {'standard': synth.config_standard, 'short': synth.config_short,
+           'long': synth.config_long, 'dense': synth.config_indel_dense}[name](seed_base)
+    return cfg
+
+
+# ----------------------------------------------------------------------------- CPU legs
+def _oracle_one(read):
+    from oracle import resquiggle_oracle as orc
+    t0 = time.perf_counter()
+    try:
+        orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                            read.read_align.decode(), read.genome_align.decode(),
+                            sort_kind='default', verbatim_clip_loop=True)
+        ok = True
+    except Exception:
+        ok = False
+    return read.n_samples if ok else 0, time.perf_counter() - t0
+
+
+def time_oracle(reads, procs):
+    """samples/s of the oracle port over `reads` with a process pool of `procs`."""
+    import multiprocessing as mp
+    if procs <= 1:
+        t0 = time.perf_counter()
+        res = [_oracle_one(r) for r in reads]
+        dt = time.perf_counter() - t0
+    else:
+        with mp.get_context('fork').Pool(procs) as pool:
+            pool.map(_oracle_one, reads[:procs])  # spin the workers up outside the timing
+            t0 = time.perf_counter()
+            res = pool.map(_oracle_one, reads, chunksize=1)
+            dt = time.perf_counter() - t0
+    samples = sum(s for s, _ in res)
+    cpu_s = sum(t for _, t in res)
+    return samples / dt, dt, samples, cpu_s
+
+
+def reference_arm(args):
+    """The reference's own CPU implementation of the path: the Python-3 oracle port (the Py2
+    original cannot run in this image), all host cores, bounded sample per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = host_cores()
+    cfg = workload_config(args.config, 2000)
+    n = max(4, 4 * cores if args.ref_reads is None else args.ref_reads)
+    genome = synth.make_genome(cfg.genome_len)
+    levels = synth.kmer_levels(cfg)
+    reads = [synth.make_read(genome, levels, cfg, i) for i in range(n)]
+    for _ in range(args.warmup):
+        time_oracle(reads[:max(cores, 1)], cores)
+    tot_s, tot_t = 0, 0.0
+    for _ in range(args.steps):
+        _, dt, samples, _ = time_oracle(reads, cores)
+        tot_s += samples
+        tot_t += dt
+    value = tot_s / tot_t
+    sample = '%d synthetic %s reads per step (%d samples), oracle port with verbatim Python clip loop' % (
+        n, args.config, tot_s // max(args.steps, 1))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * tot_t / max(args.steps, 1),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'reads_per_s': n * args.steps / tot_t,
+        'config': {'workload': workload_name(args), 'sample': sample},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return ('BASELINE.json configs[1]: %d synthetic ~%s reads per GPU preloaded in HBM '
+            '(config "%s", %d unique reads x device-side +-2 DAC noise replicas)' % (
+                args.reads, {'standard': '10 kb / ~89k-sample', 'short': '4.5 kb / ~40k-sample',
+                             'long': '100 kb / ~0.9M-sample', 'dense': '10 kb indel-dense'}[args.config],
+                args.config, min(args.unique, args.reads)))
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ('timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []   # (wall-clock arrival time, csv line)
+        self.window = [None, None]
+
+    def mark_begin(self):
+        self.window[0] = time.time()
+
+    def mark_end(self):
+        self.window[1] = time.time()
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-i', str(self.index), '-lms', '200'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap')
+        lo, hi = self.window
+        inside = [ln for t, ln in self.lines if lo is not None and hi is not None and lo <= t <= hi + 0.25]
+        scope = 'timed region'
+        if len(inside) < 2:  # region shorter than the sampling period: use every sample under load
+            inside = [ln for _, ln in self.lines]
+            scope = 'warm-up + timed region'
+        for ln in inside:
+            parts = [p.strip() for p in ln.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower() == 'active':
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': float(max(smax)) if smax else None,
+                'power_w_max': float(max(power)) if power else None,
+                'samples': len(sm), 'scope': scope, 'reasons': sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_device_batch(engine, host_batch, reps, rank):
+    """Tile the unique reads `reps` times on the device; replica k > 0 gets its own +-2 DAC
+    noise so every read is distinct work (replica 0 stays exact for the oracle spot check)."""
+    import torch
+    from nanoraw_b200.batch import ReadBatch
+    from nanoraw_b200.engine import DeviceBatch
+    dev = engine.device
+    U = host_batch.n_reads
+    t = {}
+    small = engine.upload(host_batch)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    for name in ('raw', 'starts', 'read_align', 'genome_align'):
+        src = small.t[name]
+        big = torch.empty(src.numel() * reps, dtype=src.dtype, device=dev)
+        for k in range(reps):
+            dst = big[k * src.numel():(k + 1) * src.numel()]
+            dst.copy_(src)
+            if name == 'raw' and k > 0:
+                noise = torch.randint(-2, 3, (src.numel(),), device=dev, generator=gen, dtype=torch.int16)
+                dst.add_(noise)
+        t[name] = big
+    for name, data in (('raw_off', 'raw'), ('starts_off', 'starts'), ('align_off', 'read_align')):
+        off = small.t[name]
+        n = small.t[data].numel()
+        parts = [off[:-1] + k * n for k in range(reps)] + [torch.tensor([reps * n], dtype=off.dtype, device=dev)]
+        t[name] = torch.cat(parts)
+    t['read_start'] = small.t['read_start'].repeat(reps)
+    total_align = host_batch.total_align * reps
+    n_samples = torch.from_numpy(host_batch.n_samples).to(dev).repeat(reps)
+    db = DeviceBatch.from_tensors(t, U * reps, total_align, dev, host=None)
+    del small
+    return db, n_samples
+
+
+def spot_check(engine, host_batch, reads, out_dev, n_check=2):
+    """replica 0 of the big batch is the unperturbed unique set: compare a couple of reads with
+    the oracle (not timed; the real parity suite is tests/ -m gpu)."""
+    from oracle import resquiggle_oracle as orc
+    import torch
+    bad = 0
+    for r in range(min(n_check, len(reads))):
+        read = reads[r]
+        want = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                                   read.read_align.decode(), read.genome_align.decode())
+        o = int(host_batch.align_off[r])
+        nb = int(out_dev.n_bases[r].item())
+        segs = out_dev.new_segs[o + r:o + r + nb + 1].cpu().numpy()
+        mean = out_dev.norm_mean[o:o + nb].cpu().numpy()
+        if not (np.array_equal(segs, want['new_segs']) and
+                np.array_equal(mean, want['events']['norm_mean'])):
+            bad += 1
+    return bad
+
+
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.batch import ReadBatch
+    from nanoraw_b200.engine import ResquiggleEngine, ResquiggleParams, DeviceResults
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+        torch.cuda.set_device(0)
+    engine = ResquiggleEngine()
+    lib = engine.lib
+    dev = engine.device
+    params = ResquiggleParams()
+    pc = params.to_c()
+
+    # ---- synthetic reads: `unique` per rank on the host, tiled to `reads` on the device
+    unique = min(args.unique, args.reads)
+    reps = max(1, args.reads // unique)
+    n_reads = unique * reps
+    cfg = workload_config(args.config, 2000 + rank * unique)
+    t0 = time.perf_counter()
+    reads = synth.make_reads_parallel(unique, cfg)
+    host_batch = ReadBatch.from_reads(reads)
+    log('[rank %d] generated %d unique reads in %.1fs (%d samples)' % (
+        rank, unique, time.perf_counter() - t0, int(host_batch.n_samples.sum())))
+    db, n_samples = build_device_batch(engine, host_batch, reps, rank)
+    out = DeviceResults(db.n_reads, db.total_align, dev)
+    ws = engine.workspace(db.n_reads, db.total_align, pc)
+    torch.cuda.synchronize()
+    log('[rank %d] device batch: %d reads, inputs %.2f GB, outputs %.2f GB, workspace %.2f GB' % (
+        rank, db.n_reads, db.device_bytes() / 1e9, out.device_bytes() / 1e9, ws.numel() / 1e9))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the timed kernel-only region
+    sampler = ClockSampler(local)
+    sampler.start()
+    for _ in range(args.warmup):
+        engine.run_device(db, pc, out=out, workspace=ws)
+    torch.cuda.synchronize()
+    bad = spot_check(engine, host_batch, reads, out) if rank == 0 else 0
+    barrier()
+    sampler.mark_begin()
+    launches0 = lib.nrq_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stage_ms = np.zeros(4)
+    ev0.record()
+    for _ in range(args.steps):
+        stage_ms += np.array(engine.run_device_profiled(db, pc, out, ws))
+    ev1.record()
+    barrier()
+    sampler.mark_end()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = lib.nrq_launch_count() - launches0
+    clocks = sampler.stop()
+    stage_ms /= max(args.steps, 1)
+
+    ok = (out.status[:db.n_reads] == 0)
+    samples_ok = int((n_samples * ok).sum().item())
+    reads_ok = int(ok.sum().item())
+    # accounting totals for the roofline (per launch = per step)
+    tot = {
+        'S': int(n_samples.sum().item()),
+        'Br1': int(db.t['starts'].numel()),
+        'A': int(db.total_align),
+        'Bg': int(out.n_bases[:db.n_reads].sum().item()),
+        'I': int(out.n_indels[:db.n_reads].sum().item()),
+        'S_reg': int(out.region_samples[:db.n_reads].sum().item()),
+        'R': db.n_reads,
+    }
+
+    # ---- e2e: host buffers through the C-ABI host entry point, copies inside the timed region
+    e2e_samples, e2e_ms, h2d, d2h = e2e_leg(args, lib, _lib, host_batch, pc, local, barrier)
+
+    # ---- reduce over ranks: max time, summed work
+    vals = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
+    sums = torch.tensor([samples_ok, reads_ok, e2e_samples, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+    elapsed_ms, e2e_ms = vals.tolist()
+    samples_all, reads_all, e2e_samples_all, launches_all = sums.tolist()
+
+    if rank == 0:
+        ms_per_step = elapsed_ms / max(args.steps, 1)
+        value = samples_all / (ms_per_step / 1e3)
+        peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(peaks_path):
+            peak = float(json.load(open(peaks_path))['hbm_gbs'])
+            peak_src = 'MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)'
+        else:
+            peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
+        stage_bytes = algorithmic_bytes(tot)
+        stages = {}
+        for name, ms in zip(STAGES, stage_ms):
+            gbs = stage_bytes[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            stages[name] = {'ms': float(ms), 'algorithmic_bytes': stage_bytes[name],
+                            'gbs': gbs, 'frac': gbs / peak}
+        dom = max(stages, key=lambda k: stages[k]['ms'])
+        path_gbs = stage_bytes['path'] / (float(stage_ms.sum()) * 1e-3) / 1e9
+        roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': stages[dom]['gbs'], 'peak': peak,
+                    'unit': 'GB/s', 'frac': stages[dom]['frac'], 'traffic': None,
+                    'peak_source': peak_src, 'share_of_step': stages[dom]['ms'] / float(stage_ms.sum()),
+                    'stages': stages,
+                    'path': {'algorithmic_bytes': stage_bytes['path'], 'achieved': path_gbs,
+                             'frac': path_gbs / peak}}
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'reads_per_s': reads_all / (ms_per_step / 1e3),
+            'config': {'workload': workload_name(args), 'reads_per_gpu': db.n_reads,
+                       'samples_per_gpu': tot['S'], 'l2': 'inputs (%.1f GB per GPU) larger than L2' % (
+                           db.device_bytes() / 1e9),
+                       'e2e': 'nrq_resquiggle_batch_host, %d reads per call, pinned host buffers; '
+                              'FAST5 I/O not included (no HDF5 library in the image)' % host_batch.n_reads,
+                       'failed_reads': int(db.n_reads * world - reads_all),
+                       'oracle_spot_check_mismatches': bad},
+            'e2e': {'value': e2e_samples_all / (e2e_ms / 1e3) if e2e_ms > 0 else None, 'unit': UNIT,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+            'gpu_launches': int(launches_all),
+            'clocks': clocks,
+            'roofline': roofline,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_baseline_leg(args, reads)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def algorithmic_bytes(t):
+    """Compulsory bytes per launch (every input read once, every output written once); DESIGN.md
+    section 'Roofline accounting' states the per-unit figures."""
+    return {
+        # alignment rows read twice is NOT compulsory: count once; indel int4 + bases written
+        'k_align_scan': 2 * t['A'] + 16 * t['I'] + t['Bg'] + 12 * t['R'],
+        'k_norm_stats': 2 * t['S'] + 32 * t['R'],
+        'k_resegment': 2 * t['S_reg'] + 4 * t['Br1'] + 16 * t['I'] + 4 * (t['Bg'] + t['R']) + 32 * t['R'],
+        'k_event_table': 2 * t['S'] + 4 * (t['Bg'] + t['R']) + 24 * t['Bg'] + 32 * t['R'],
+        # 2S + 4(Br+1) + alignment bytes + Bg + 25 Bg + 32 per read
+        'path': 2 * t['S'] + 4 * t['Br1'] + 2 * t['A'] + t['Bg'] + 25 * t['Bg'] + 32 * t['R'],
+    }
+
+
+def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
+    import ctypes as C
+    import torch
+    from nanoraw_b200.batch import ReadBatch
+    R, A = host_batch.n_reads, host_batch.total_align
+    keep = []
+
+    def pinned(arr):
+        t = torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()
+        keep.append(t)
+        return t
+
+    hb = _lib.NrqBatch()
+    hb.n_reads = R
+    h2d = 0
+    for f in ReadBatch.FIELDS:
+        t = pinned(getattr(host_batch, f))
+        h2d += t.numel() * t.element_size()
+        setattr(hb, f, t.data_ptr())
+    outs = {'status': (R, np.int32), 'n_bases': (R, np.int32), 'n_indels': (R, np.int32),
+            'scale_values': (4 * R, np.float64), 'new_segs': (A + R, np.int32),
+            'norm_mean': (A, np.float64), 'norm_stdev': (A, np.float64), 'ev_start': (A, np.uint32),
+            'ev_length': (A, np.uint32), 'ev_base': (A, np.uint8), 'region_samples': (R, np.int32)}
+    hr = _lib.NrqResults()
+    d2h = 0
+    host_out = {}
+    for k, (n, dt) in outs.items():
+        t = pinned(np.zeros(n, dtype=dt).view(np.int32 if dt == np.uint32 else dt))
+        host_out[k] = t
+        d2h += t.numel() * t.element_size()
+        setattr(hr, k, t.data_ptr())
+    h = lib.nrq_create(device_index)
+    if not h:
+        raise RuntimeError('nrq_create failed: ' + lib.nrq_last_error().decode())
+    for _ in range(max(args.warmup, 1)):
+        _lib.check(lib.nrq_resquiggle_batch_host(h, C.byref(hb), C.byref(pc), C.byref(hr)), 'e2e warm-up')
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        _lib.check(lib.nrq_resquiggle_batch_host(h, C.byref(hb), C.byref(pc), C.byref(hr)), 'e2e step')
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / max(args.e2e_steps, 1)
+    lib.nrq_destroy(h)
+    status = host_out['status'].numpy()
+    samples = int(host_batch.n_samples[status == 0].sum())
+    return samples, e2e_ms, h2d, d2h
+
+
+def cpu_baseline_leg(args, reads):
+    cores = host_cores()
+    n = min(len(reads), max(8, 2 * cores if args.cpu_reads is None else args.cpu_reads))
+    value, dt, samples, cpu_s = time_oracle(reads[:n], cores)
+    return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d reads of the same workload (%d samples), %.1f s wall, %.1f CPU-s; oracle port '
+                      'with verbatim Python clip loop' % (n, samples, dt, cpu_s),
+            'per_core': samples / cpu_s if cpu_s > 0 else None}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
+    ap.add_argument('--reads', type=int, default=100_000, help='reads per GPU')
+    ap.add_argument('--unique', type=int, default=2000, help='distinct synthetic reads generated on the host')
+    ap.add_argument('--config', default='standard', choices=('standard', 'short', 'long', 'dense'))
+    ap.add_argument('--e2e-steps', type=int, default=5)
+    ap.add_argument('--cpu-reads', type=int, default=None)
+    ap.add_argument('--ref-reads', type=int, default=None)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -107,6 +107,7 @@ typedef struct nrq_results {
   uint32_t* ev_start;     /* [align_off[R]] */
   uint32_t* ev_length;    /* [align_off[R]] */
   uint8_t*  ev_base;      /* [align_off[R]] */
+  int32_t*  region_samples; /* [R] or NULL: samples covered by the final indel groups (accounting aid) */
 } nrq_results;
 
 int  nrq_version(void);
@@ -138,11 +139,12 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
                          const int64_t* norm_off, double* norm_signal, void* stream);
 
 /* a3-a6: get_indel_groups + splice (resquiggle.py:203-316, 362-387) -> new_segs, status.
- * group_scratch: int32[4*indel_capacity]; big_scratch: see nrq_workspace_bytes. */
+ * group_scratch: int32[4*indel_capacity]; big_scratch: see nrq_workspace_bytes; region_samples may be NULL. */
 int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                   const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
                   int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
-                  int32_t* work_counter, int32_t* status, int32_t* new_segs, void* stream);
+                  int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
+                  void* stream);
 
 /* a7: per-base mean / sd / start / length / base (resquiggle.py:60-70). */
 int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale_values,
@@ -154,6 +156,12 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
  * resquiggle.py:424-433, minus FAST5 I/O).  workspace: device, >= nrq_workspace_bytes(). */
 int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
                          void* workspace, int64_t workspace_bytes, void* stream);
+
+/* nrq_resquiggle_batch with CUDA events recorded on `stream` around each stage; waits for the batch and
+ * writes the device time in ms of {indel scan (a2), order statistics (a1), re-segmentation (a3-a6),
+ * event table (a7)} to stage_ms[4].  Measurement aid for bench.py. */
+int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
+                                 void* workspace, int64_t workspace_bytes, void* stream, float* stage_ms);
 
 /* Same, but every pointer in `b` and `out` is a HOST pointer (pinned memory recommended).  The library
  * stages through device buffers it owns (grown on demand, per handle) and returns after the results

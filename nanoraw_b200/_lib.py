@@ -34,7 +34,7 @@ class NrqResults(C.Structure):
         ('status', C.c_void_p), ('n_bases', C.c_void_p), ('n_indels', C.c_void_p),
         ('scale_values', C.c_void_p), ('new_segs', C.c_void_p), ('norm_mean', C.c_void_p),
         ('norm_stdev', C.c_void_p), ('ev_start', C.c_void_p), ('ev_length', C.c_void_p),
-        ('ev_base', C.c_void_p)]
+        ('ev_base', C.c_void_p), ('region_samples', C.c_void_p)]
 
 
 # every symbol include/nrq.h declares: (restype, argtypes)
@@ -48,11 +48,14 @@ SYMBOLS = {
     'nrq_norm_stats': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P]),
     'nrq_normalize_signal': (C.c_int, [C.POINTER(NrqBatch), _P, _P, _P, _P, _P]),
     'nrq_resegment': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
-                                C.c_int64, _P, _P, _P, _P]),
+                                C.c_int64, _P, _P, _P, _P, _P]),
     'nrq_event_table': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P]),
     'nrq_resquiggle_batch': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams),
                                        C.POINTER(NrqResults), _P, C.c_int64, _P]),
+    'nrq_resquiggle_batch_profile': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams),
+                                               C.POINTER(NrqResults), _P, C.c_int64, _P,
+                                               C.POINTER(C.c_float)]),
     'nrq_create': (_P, [C.c_int32]),
     'nrq_destroy': (None, [_P]),
     'nrq_resquiggle_batch_host': (C.c_int, [_P, C.POINTER(NrqBatch), C.POINTER(NrqParams),

@@ -48,8 +48,6 @@ int resegment_grid(int n_reads) {
   return need < cached ? (need > 0 ? need : 1) : cached;
 }
 
-int resegment_grid_max() { return resegment_grid(1 << 30); }
-
 struct Workspace {
   int64_t* indel_off;
   int32_t* work_counter;
@@ -176,7 +174,7 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
   if (int e = check_batch(b)) return e;
   if (!scale_values || !status || !norm_off || !norm_signal) return fail("nrq_normalize_signal: NULL argument");
   if (b->n_reads == 0) return 0;
-  dim3 grid(64, b->n_reads);
+  dim3 grid(b->n_reads, 16);
   nrq::k_normalize_signal<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(*b, scale_values, status,
                                                                                norm_off, norm_signal);
   NRQ_CHECK_LAUNCH("k_normalize_signal");
@@ -186,7 +184,8 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
 int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                   const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
                   int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
-                  int32_t* work_counter, int32_t* status, int32_t* new_segs, void* stream) {
+                  int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
+                  void* stream) {
   if (int e = check_batch(b)) return e;
   if (int e = check_params(p)) return e;
   if (!scale_values || !indel_off || !indels || !n_bases || !group_scratch || !work_counter || !status ||
@@ -202,7 +201,7 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
   if (e != cudaSuccess) return fail("memset work_counter", e);
   nrq::k_resegment<<<grid, nrq::kSegWarps * 32, 0, s>>>(
       *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), n_bases,
-      reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs);
+      reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs, region_samples);
   NRQ_CHECK_LAUNCH("k_resegment");
   return 0;
 }
@@ -223,8 +222,8 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
   return 0;
 }
 
-int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_results* out, void* workspace,
-                         int64_t workspace_bytes, void* stream) {
+static int resquiggle_batch_impl(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
+                                 void* workspace, int64_t workspace_bytes, void* stream, cudaEvent_t* ev) {
   if (int e = check_batch(b)) return e;
   if (int e = check_params(p)) return e;
   if (!out || !out->status || !out->n_bases || !out->n_indels || !out->scale_values || !out->new_segs ||
@@ -239,17 +238,46 @@ int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_resu
   int64_t indel_cap = spare / 32;
   Workspace w = carve(workspace, b->n_reads, 0, p, indel_cap);
   if (w.bytes > workspace_bytes) return fail("nrq_resquiggle_batch: workspace too small");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], s); };
 
+  mark(0);
   if (int e = nrq_find_indels(b, out->status, out->n_indels, out->n_bases, w.indel_off, w.indels, w.indel_cap,
                               out->ev_base, stream))
     return e;
+  mark(1);
   if (int e = nrq_norm_stats(b, p, out->status, out->scale_values, stream)) return e;
+  mark(2);
   if (int e = nrq_resegment(b, p, out->scale_values, w.indel_off, w.indels, out->n_bases, w.groups, w.big,
-                            w.big_doubles, w.work_counter, out->status, out->new_segs, stream))
+                            w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, stream))
     return e;
+  mark(3);
   if (int e = nrq_event_table(b, p, out->scale_values, out->n_bases, out->new_segs, out->status, out->norm_mean,
                               out->norm_stdev, out->ev_start, out->ev_length, out->ev_base, stream))
     return e;
+  mark(4);
+  return 0;
+}
+
+int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_results* out, void* workspace,
+                         int64_t workspace_bytes, void* stream) {
+  return resquiggle_batch_impl(b, p, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
+                                 void* workspace, int64_t workspace_bytes, void* stream, float* stage_ms) {
+  if (!stage_ms) return fail("nrq_resquiggle_batch_profile: stage_ms is NULL");
+  thread_local cudaEvent_t ev[5];
+  thread_local bool have = false;
+  if (!have) {
+    for (auto& e : ev)
+      if (cudaEventCreate(&e) != cudaSuccess) return fail("cudaEventCreate failed");
+    have = true;
+  }
+  if (int e = resquiggle_batch_impl(b, p, out, workspace, workspace_bytes, stream, ev)) return e;
+  cudaError_t ce = cudaEventSynchronize(ev[4]);
+  if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_profile: sync", ce);
+  for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
   return 0;
 }
 
@@ -336,6 +364,7 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
   o.ev_start = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
   o.ev_length = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
   o.ev_base = (uint8_t*)up(nullptr, (size_t)n_align);
+  o.region_samples = (int32_t*)up(nullptr, 4 * (size_t)R);
   int64_t ws_bytes = nrq_workspace_bytes(R, n_align, p);
   void* ws = up(nullptr, (size_t)ws_bytes);
   if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host: staging", err);
@@ -356,6 +385,7 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
   down(out->ev_start, o.ev_start, 4 * (size_t)n_align);
   down(out->ev_length, o.ev_length, 4 * (size_t)n_align);
   down(out->ev_base, o.ev_base, (size_t)n_align);
+  down(out->region_samples, o.region_samples, 4 * (size_t)R);
   if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host: readback", err);
   ce = cudaStreamSynchronize(s);
   if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_host: sync", ce);

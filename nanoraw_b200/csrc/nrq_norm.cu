@@ -315,13 +315,13 @@ k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __
 __global__ void __launch_bounds__(256)
 k_normalize_signal(nrq_batch b, const double* __restrict__ sv, const int32_t* __restrict__ status,
                    const int64_t* __restrict__ norm_off, double* __restrict__ out) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.x;
   int st = status[r];
   if (st != NRQ_ST_OK && st != NRQ_ST_PAST_END) return;
   ReadGeom g = read_geom(b, r);
   NormCoef c = load_coef(sv, r);
   double* o = out + norm_off[r];
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < g.n_norm; i += gridDim.x * blockDim.x)
+  for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < g.n_norm; i += gridDim.y * blockDim.x)
     o[i] = norm_value((int)g.sig[i], c);
 }
 

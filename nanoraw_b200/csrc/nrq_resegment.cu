@@ -180,7 +180,7 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
-__device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm) {
+__device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm, int& region_samples) {
   const unsigned lane = lane_id();
   const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
   int dtotal = 0;
@@ -226,6 +226,7 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       d = c.ind[grp.z].w;
       for (int j = prev_stop + (int)lane; j <= upto; j += 32) c.out[j + d] = c.t[j];
       prev_stop = grp.y;
+      region_samples += c.t[grp.y] - c.t[grp.x];
     } else {
       for (int j = prev_stop + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = c.t[j];
     }
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kSegWarps * 32)
 k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int64_t* __restrict__ indel_off,
             const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
             double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
-            int32_t* __restrict__ new_segs) {
+            int32_t* __restrict__ new_segs, int32_t* __restrict__ region_samples) {
   __shared__ double region[kSegWarps][kRegionCap + 1];
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
@@ -274,8 +275,10 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.buf_sm = region[warp];
     c.big_cap = p.big_region_cap;
     c.buf_big = big_scratch + (size_t)gwarp * (size_t)(p.big_region_cap + 1);
-    int st = resegment_read(c, p.timeout_ns, n_bases[r], g.n_norm);
+    int reg = 0;
+    int st = resegment_read(c, p.timeout_ns, n_bases[r], g.n_norm, reg);
     if (lane == 0 && st != NRQ_ST_OK) status[r] = st;
+    if (lane == 0 && region_samples) region_samples[r] = reg;
     __syncwarp();
   }
 }

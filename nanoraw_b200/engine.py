@@ -70,6 +70,18 @@ class DeviceBatch(object):
             self.t[name] = ht.to(device, non_blocking=non_blocking)
         self.c = self._struct()
 
+    @classmethod
+    def from_tensors(cls, tensors, n_reads, total_align, device, host=None):
+        """Wrap tensors that already live on `device` (bench.py builds big batches there)."""
+        self = cls.__new__(cls)
+        self.n_reads = n_reads
+        self.total_align = total_align
+        self.device = device
+        self.host = host
+        self.t = {name: tensors.get(name) for name in ReadBatch.FIELDS + ('scale_values_in',)}
+        self.c = self._struct()
+        return self
+
     def _struct(self):
         b = _lib.NrqBatch()
         b.n_reads = self.n_reads
@@ -98,6 +110,7 @@ class DeviceResults(object):
         self.ev_start = mk(A, torch.int32)    # bit pattern of uint32
         self.ev_length = mk(A, torch.int32)
         self.ev_base = mk(A, torch.uint8)
+        self.region_samples = mk(R, torch.int32)
         c = _lib.NrqResults()
         for name, _ in _lib.NrqResults._fields_:
             setattr(c, name, _ptr(getattr(self, name)))
@@ -192,6 +205,18 @@ class ResquiggleEngine(object):
         _lib.check(rc, 'nrq_resquiggle_batch')
         return out
 
+    def run_device_profiled(self, dbatch, params, out, workspace):
+        """run_device, plus the device time (ms) of each of the four stages (CUDA events on the
+        launching stream); returns after the batch has finished."""
+        pc = params.to_c() if isinstance(params, ResquiggleParams) else params
+        ms = (C.c_float * 4)()
+        with self.torch.cuda.device(self.device):
+            rc = self.lib.nrq_resquiggle_batch_profile(
+                C.byref(dbatch.c), C.byref(pc), C.byref(out.c), _ptr(workspace), workspace.numel(),
+                self._stream(), ms)
+        _lib.check(rc, 'nrq_resquiggle_batch_profile')
+        return list(ms)
+
     def download(self, dbatch, out):
         arrays = {}
         for name in DeviceResults.NAMES:
@@ -200,7 +225,7 @@ class ResquiggleEngine(object):
                 a = a.view(np.uint32)
             arrays[name] = a
         R = dbatch.n_reads
-        for name in ('status', 'n_bases', 'n_indels'):
+        for name in ('status', 'n_bases', 'n_indels', 'region_samples'):
             arrays[name] = arrays[name][:R]
         arrays['scale_values'] = arrays['scale_values'][:4 * R]
         return HostResults(dbatch.host.align_off, arrays)

@@ -51,7 +51,7 @@ def test_params_struct_layout():
     assert _lib.NrqParams.outlier_thresh.offset == 8
     assert _lib.NrqParams.timeout_ns.offset == 32
     assert C.sizeof(_lib.NrqBatch) == 80
-    assert C.sizeof(_lib.NrqResults) == 80
+    assert C.sizeof(_lib.NrqResults) == 88
 
 
 def test_engine_refuses_without_gpu():

@@ -208,7 +208,7 @@ def test_host_buffer_entry_point(engine):
             'n_indels': np.zeros(R, np.int32), 'scale_values': np.zeros(4 * R),
             'new_segs': np.zeros(A + R, np.int32), 'norm_mean': np.zeros(A), 'norm_stdev': np.zeros(A),
             'ev_start': np.zeros(A, np.uint32), 'ev_length': np.zeros(A, np.uint32),
-            'ev_base': np.zeros(A, np.uint8)}
+            'ev_base': np.zeros(A, np.uint8), 'region_samples': np.zeros(R, np.int32)}
     hr = _lib.NrqResults()
     for k, v in outs.items():
         setattr(hr, k, v.ctypes.data)
