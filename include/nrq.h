@@ -66,7 +66,9 @@ typedef struct nrq_params {
   int32_t min_seg_len;      /* min_event_obs, 4 in the reference (resquiggle.py:323) */
   int64_t timeout_ns;       /* --timeout on the device clock; <= 0: none */
   int32_t big_region_cap;   /* samples per warp of global scratch for regions that do not fit shared memory */
-  int32_t debug_flags;      /* bit0: force the general (bisection) order-statistic path in nrq_norm_stats */
+  int32_t debug_flags;      /* bit0: force the general (bisection) order-statistic path in nrq_norm_stats;
+                               bit1: event statistics in numpy's float64 summation order (bit-identical to
+                               numpy, slower) instead of exact integer prefix sums (within a few ulps) */
 } nrq_params;
 
 /* Ragged batch, inputs.  R = n_reads.

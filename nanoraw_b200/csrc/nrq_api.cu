@@ -216,8 +216,12 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
     return fail("nrq_event_table: NULL argument");
   (void)ev_base;  // written by nrq_find_indels
   if (b->n_reads == 0) return 0;
-  nrq::k_event_table<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
-      *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
+  if (p->debug_flags & 2)
+    nrq::k_event_table_exact<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
+  else
+    nrq::k_event_table<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   NRQ_CHECK_LAUNCH("k_event_table");
   return 0;
 }

@@ -28,6 +28,7 @@ class ResquiggleParams:
     min_event_obs: int = 4
     given_limits: bool = False
     big_region_cap: int = 16384
+    exact_stats: bool = False            # event mean/sd in numpy's summation order (bit-identical, slower)
     debug_flags: int = 0
 
     def to_c(self):
@@ -41,7 +42,7 @@ class ResquiggleParams:
         p.min_seg_len = int(self.min_event_obs)
         p.timeout_ns = 0 if self.timeout is None else int(self.timeout * 1e9)
         p.big_region_cap = int(self.big_region_cap)
-        p.debug_flags = int(self.debug_flags)
+        p.debug_flags = int(self.debug_flags) | (2 if self.exact_stats else 0)
         return p
 
 
