@@ -220,7 +220,8 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
     nrq::k_event_table_exact<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   else
-    nrq::k_event_table<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+    nrq::k_event_table<<<(b->n_reads + nrq::kEvWarps - 1) / nrq::kEvWarps, nrq::kEvWarps * 32, 0,
+                         static_cast<cudaStream_t>(stream)>>>(
         *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   NRQ_CHECK_LAUNCH("k_event_table");
   return 0;

@@ -1,8 +1,8 @@
 // K3 -- per-base event statistics (nanoraw/resquiggle.py:60-70): mean and (population) standard
 // deviation of the normalised signal inside each new segment, plus start / length.
 //
-// Two kernels.  k_event_table (default) streams the read once in 2048-sample tiles and gets
-// every base's sums from exact integer prefix sums of the DAC codes (see below).
+// Two kernels.  k_event_table (default): one warp streams one read once, 256 samples per step, and
+// gets every base's sums from exact integer prefix sums of the DAC codes (see below).
 // k_event_table_exact (debug_flags bit 1) replays numpy's float64 summation order and is
 // bit-identical to numpy; it is what the integer kernel is validated against.
 //
@@ -158,7 +158,8 @@ k_event_table_exact(nrq_batch b, nrq_params p, const double* __restrict__ sv, co
 // coalesced, with no per-base loops.  The numerator n_u S2 - S1^2 is formed in 128-bit integers:
 // no cancellation.  Results differ from numpy's (which sums the individually rounded x_i) by a few
 // ulps -- far inside the 1e-9 contract -- and are checked against the exact kernel in tests.
-constexpr int kTile = kEvThreads * 8;  // samples per tile: one 128-bit load per thread
+constexpr int kEvWarps = 8;   // reads per CTA: one warp streams one read
+constexpr int kSub = 32 * 8;  // samples per step: one 128-bit load per lane
 
 struct EvClass {
   int u_lo, u_hi;  // DAC codes in [u_lo, u_hi] are not clipped
@@ -166,13 +167,13 @@ struct EvClass {
   double below_val, above_val;  // value taken by codes below u_lo / above u_hi
 };
 
-__device__ __forceinline__ void ev_accum(int v, bool valid, const EvClass& k, int& s1,
+__device__ __forceinline__ void ev_accum(int v, bool valid, int u_lo, int u_hi, int pivot, int& s1,
                                          unsigned long long& s2, unsigned& cnt) {
-  bool unc = valid && v >= k.u_lo && v <= k.u_hi;
-  int d = unc ? v - k.pivot : 0;
+  bool unc = valid && v >= u_lo && v <= u_hi;
+  int d = unc ? v - pivot : 0;
   s1 += d;
   s2 += (unsigned long long)((long long)d * (long long)d);
-  cnt += (valid && v < k.u_lo ? 1u : 0u) + (valid && v > k.u_hi ? 65536u : 0u);
+  cnt += (valid && v < u_lo ? 1u : 0u) + (valid && v > u_hi ? 65536u : 0u);
 }
 
 __device__ __forceinline__ int unpack16(const int4& q, int j) {
@@ -180,104 +181,108 @@ __device__ __forceinline__ int unpack16(const int4& q, int j) {
   return (int)(short)((j & 1) ? (w >> 16) : (w & 0xffff));
 }
 
-struct EvPrefix {
-  long long s1;
-  unsigned long long s2;
-  int cl, ch;
-};
+// 1/y for y >= 1 well inside float range: float seed + two Newton steps (a few ulps)
+__device__ __forceinline__ double ev_rcp(double y) {
+  double r = (double)__frcp_rn((float)y);
+  r = fma(r, fma(-y, r, 1.0), r);
+  r = fma(r, fma(-y, r, 1.0), r);
+  return r;
+}
 
-__global__ void __launch_bounds__(kEvThreads)
+__device__ __forceinline__ double ev_sqrt(double y) {
+  if (!(y > 1e-30 && y < 1e30)) return sqrt(y);
+  double r = (double)rsqrtf((float)y);
+  const double h = 0.5 * y;
+  r = r * fma(-h * r, r, 1.5);
+  r = r * fma(-h * r, r, 1.5);
+  double s = y * r;
+  return fma(fma(-s, s, y), 0.5 * r, s);
+}
+
+__device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_sample) {
+  EvClass k;
+  k.u_lo = -32768; k.u_hi = 32767;
+  k.below_val = 0.0; k.above_val = 0.0;
+  if (coef.clip) {
+    // x is monotone in the DAC code, so each clip limit is one integer threshold.  Start from the
+    // real-valued estimate, then settle it with the exact per-code evaluation (nanoraw_helper.py:248).
+    const bool inc = coef.scale > 0.0;
+    auto xval = [&](int v) { return __ddiv_rn(__dsub_rn((double)v, coef.shift), coef.scale); };
+    // codes clipped on the low-code side / high-code side (which limit that is depends on the sign of scale)
+    auto low_side = [&](int v) { double x = xval(v); return inc ? (x < coef.lo) : (x > coef.hi); };
+    auto high_side = [&](int v) { double x = xval(v); return inc ? (x > coef.hi) : (x < coef.lo); };
+    double e0 = coef.shift + (inc ? coef.lo : coef.hi) * coef.scale;
+    double e1 = coef.shift + (inc ? coef.hi : coef.lo) * coef.scale;
+    int lo = (int)fmin(fmax(floor(e0), -32768.0), 32768.0);
+    int hi = (int)fmin(fmax(ceil(e1), -32769.0), 32767.0);
+    while (lo > -32768 && !low_side(lo - 1)) --lo;   // u_lo = smallest code not clipped on the low side
+    while (lo <= 32767 && low_side(lo)) ++lo;
+    while (hi < 32767 && !high_side(hi + 1)) ++hi;   // u_hi = largest code not clipped on the high side
+    while (hi >= -32768 && high_side(hi)) --hi;
+    k.u_lo = lo; k.u_hi = hi;
+    k.below_val = inc ? coef.lo : coef.hi;
+    k.above_val = inc ? coef.hi : coef.lo;
+  }
+  long long mid = ((long long)max(k.u_lo, -32768) + (long long)min(k.u_hi, 32767)) / 2;
+  k.pivot = coef.clip ? (int)mid : pivot_sample;
+  return k;
+}
+
+__global__ void __launch_bounds__(kEvWarps * 32)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
               const int32_t* __restrict__ new_segs, const int32_t* __restrict__ status,
               double* __restrict__ norm_mean, double* __restrict__ norm_stdev,
               uint32_t* __restrict__ ev_start, uint32_t* __restrict__ ev_length) {
-  __shared__ int4 raw_tile[kEvThreads];
-  __shared__ int ex1[kEvThreads];
-  __shared__ unsigned long long ex2[kEvThreads];
-  __shared__ unsigned exc[kEvThreads];
-  __shared__ int w1[kEvThreads / 32];
-  __shared__ unsigned long long w2[kEvThreads / 32];
-  __shared__ unsigned wc[kEvThreads / 32];
-  __shared__ EvPrefix pb[kEvThreads + 1];  // pb[0] = prefix at the boundary before this chunk
-  __shared__ EvClass kcls;
-
-  const int r = blockIdx.x;
-  if (status[r] != NRQ_ST_OK) return;
-  const int tid = threadIdx.x;
-  const unsigned lane = lane_id();
-  const int warp = tid >> 5;
+  const int r = blockIdx.x * kEvWarps + (threadIdx.x >> 5);
+  if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
+  const int lane = (int)lane_id();
   ReadGeom g = read_geom(b, r);
-  NormCoef coef = load_coef(sv, r);
+  const NormCoef coef = load_coef(sv, r);
   const int nb = n_bases[r];
   const int32_t* segs = new_segs + b.align_off[r] + r;
   const size_t off = (size_t)b.align_off[r];
   const int n_norm = g.n_norm;
 
-  if (tid == 0) {
-    EvClass k;
-    k.u_lo = -32768; k.u_hi = 32767;
-    k.below_val = 0.0; k.above_val = 0.0;
-    if (coef.clip) {
-      // x is monotone in the DAC code, so each clip limit is one integer threshold.  Start from the
-      // real-valued estimate, then settle it with the exact per-code evaluation (nanoraw_helper.py:248).
-      const bool inc = coef.scale > 0.0;
-      auto xval = [&](int v) { return __ddiv_rn(__dsub_rn((double)v, coef.shift), coef.scale); };
-      // codes clipped on the low-code side / high-code side (which limit that is depends on the sign of scale)
-      auto low_side = [&](int v) { double x = xval(v); return inc ? (x < coef.lo) : (x > coef.hi); };
-      auto high_side = [&](int v) { double x = xval(v); return inc ? (x > coef.hi) : (x < coef.lo); };
-      double e0 = coef.shift + (inc ? coef.lo : coef.hi) * coef.scale;
-      double e1 = coef.shift + (inc ? coef.hi : coef.lo) * coef.scale;
-      int lo = (int)fmin(fmax(floor(e0), -32768.0), 32768.0);
-      int hi = (int)fmin(fmax(ceil(e1), -32769.0), 32767.0);
-      while (lo > -32768 && !low_side(lo - 1)) --lo;   // u_lo = smallest code not clipped on the low side
-      while (lo <= 32767 && low_side(lo)) ++lo;
-      while (hi < 32767 && !high_side(hi + 1)) ++hi;   // u_hi = largest code not clipped on the high side
-      while (hi >= -32768 && high_side(hi)) --hi;
-      k.u_lo = lo; k.u_hi = hi;
-      k.below_val = inc ? coef.lo : coef.hi;
-      k.above_val = inc ? coef.hi : coef.lo;
-    }
-    long long mid = ((long long)max(k.u_lo, -32768) + (long long)min(k.u_hi, 32767)) / 2;
-    k.pivot = coef.clip ? (int)mid : (int)g.sig[n_norm / 2];
-    kcls = k;
-  }
-  __syncthreads();
-  const EvClass k = kcls;
-  const double c_off = __dsub_rn((double)k.pivot, coef.shift);
+  const EvClass k = ev_classify(coef, (int)g.sig[n_norm / 2]);  // every lane: a handful of divisions
+  const int u_lo = k.u_lo, u_hi = k.u_hi, pivot = k.pivot;
+  const double c_off = __dsub_rn((double)pivot, coef.shift);
+  const double inv_scale = 1.0 / coef.scale;
+  const double inv_scale2 = inv_scale * inv_scale;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
-  // tiles are laid out on 16-byte boundaries of the raw buffer: sample i sits at slot i + a
+  // steps are laid out on 16-byte boundaries of the raw buffer: sample i sits at slot i + a
   const int a = (int)(((uintptr_t)g.sig >> 1) & 7);
   const int16_t* base_al = g.sig - a;
   const int16_t* raw_end = b.raw + b.raw_off[b.n_reads];
-  EvPrefix run = {0, 0ull, 0, 0};  // prefix at the start of the current tile
-  int cur = 0;                     // next boundary to resolve (0 .. nb)
-  if (tid == 0) pb[0] = run;
+  // running prefix at the start of the current step, and prefix at the last resolved boundary
+  long long run1 = 0, prev1 = 0;
+  unsigned long long run2 = 0, prev2 = 0;
+  int runl = 0, runh = 0, prevl = 0, prevh = 0;
+  int cur = 0;  // next boundary to resolve (0 .. nb)
 
-  for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kTile) {
-    // ---- A: load 8 samples, thread totals
-    const int slot = tile0 + 8 * tid;  // aligned sample slot of this thread's chunk
+  for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
+    // ---- load 8 samples, lane totals
+    const int slot = tile0 + 8 * lane;
     int4 q = make_int4(0, 0, 0, 0);
     if (slot < n_norm + a) {
       const int16_t* ptr = base_al + slot;
       if (ptr + 8 <= raw_end) q = __ldg(reinterpret_cast<const int4*>(ptr));
       else {
-        short tmp[8];
-        for (int j = 0; j < 8; ++j) tmp[j] = (ptr + j < raw_end) ? ptr[j] : (short)0;
-        q = make_int4((tmp[0] & 0xffff) | (tmp[1] << 16), (tmp[2] & 0xffff) | (tmp[3] << 16),
-                      (tmp[4] & 0xffff) | (tmp[5] << 16), (tmp[6] & 0xffff) | (tmp[7] << 16));
+        int w[4] = {0, 0, 0, 0};
+        for (int j = 0; j < 8; ++j)
+          if (ptr + j < raw_end) w[j >> 1] |= ((int)(unsigned short)ptr[j]) << (16 * (j & 1));
+        q = make_int4(w[0], w[1], w[2], w[3]);
       }
     }
-    raw_tile[tid] = q;
     int s1 = 0;
     unsigned long long s2 = 0;
     unsigned cnt = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       int i = slot + j - a;
-      ev_accum(unpack16(q, j), i >= 0 && i < n_norm, k, s1, s2, cnt);
+      ev_accum(unpack16(q, j), i >= 0 && i < n_norm, u_lo, u_hi, pivot, s1, s2, cnt);
     }
-    // ---- B: block exclusive scan of (s1, s2, cnt)
+    // ---- warp scan of (s1, s2, cnt): exclusive prefixes ex*, step totals tot*
     int i1 = s1;
     unsigned long long i2 = s2;
     unsigned ic = cnt;
@@ -286,27 +291,19 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       int t1 = __shfl_up_sync(0xffffffffu, i1, o);
       unsigned long long t2 = __shfl_up_sync(0xffffffffu, i2, o);
       unsigned tc = __shfl_up_sync(0xffffffffu, ic, o);
-      if ((int)lane >= o) { i1 += t1; i2 += t2; ic += tc; }
+      if (lane >= o) { i1 += t1; i2 += t2; ic += tc; }
     }
-    if (lane == 31) { w1[warp] = i1; w2[warp] = i2; wc[warp] = ic; }
-    __syncthreads();
-    int b1 = 0, tot1 = 0;
-    unsigned long long b2 = 0, tot2 = 0;
-    unsigned bc = 0, totc = 0;
-#pragma unroll
-    for (int w = 0; w < kEvThreads / 32; ++w) {
-      if (w < warp) { b1 += w1[w]; b2 += w2[w]; bc += wc[w]; }
-      tot1 += w1[w]; tot2 += w2[w]; totc += wc[w];
-    }
-    ex1[tid] = b1 + i1 - s1;
-    ex2[tid] = b2 + i2 - s2;
-    exc[tid] = bc + ic - cnt;
-    __syncthreads();
+    const int ex1 = i1 - s1;
+    const unsigned long long ex2 = i2 - s2;
+    const unsigned exc = ic - cnt;
+    const int tot1 = __shfl_sync(0xffffffffu, i1, 31);
+    const unsigned long long tot2 = __shfl_sync(0xffffffffu, i2, 31);
+    const unsigned totc = __shfl_sync(0xffffffffu, ic, 31);
 
-    // ---- C/D: boundaries that fall inside this tile, 256 at a time
-    const int tile_end = tile0 + kTile;  // in slots
+    // ---- boundaries that fall inside this step, 32 at a time
+    const int tile_end = tile0 + kSub;
     for (;;) {
-      int bidx = cur + tid;
+      const int bidx = cur + lane;
       int pos = 0;
       bool inb = false;
       if (bidx <= nb) {
@@ -314,61 +311,78 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         pos = (bidx == 0) ? 0 : (bidx == nb ? n_norm : segs[bidx]);
         inb = pos + a < tile_end;
       }
-      int cntb = __syncthreads_count(inb);
-      if (inb) {
-        int sl = pos + a - tile0;  // slot inside the tile (>= 0 because boundaries ascend)
-        if (sl < 0) sl = 0;
-        int t = sl >> 3, jn = sl & 7;
-        int4 qq = raw_tile[t];
-        int p1 = 0;
-        unsigned long long p2 = 0;
-        unsigned pc = 0;
+      const unsigned bal = __ballot_sync(0xffffffffu, inb);
+      const int cntb = __popc(bal);
+      if (cntb == 0) break;
+      int sl = inb ? pos + a - tile0 : 0;  // slot inside the step
+      if (sl < 0) sl = 0;
+      const int t = sl >> 3, jn = sl & 7;
+      int4 qq;
+      qq.x = __shfl_sync(0xffffffffu, q.x, t);
+      qq.y = __shfl_sync(0xffffffffu, q.y, t);
+      qq.z = __shfl_sync(0xffffffffu, q.z, t);
+      qq.w = __shfl_sync(0xffffffffu, q.w, t);
+      const int tex1 = __shfl_sync(0xffffffffu, ex1, t);
+      const unsigned long long tex2 = __shfl_sync(0xffffffffu, ex2, t);
+      const unsigned texc = __shfl_sync(0xffffffffu, exc, t);
+      int p1 = 0;
+      unsigned long long p2 = 0;
+      unsigned pc = 0;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          int i = tile0 + 8 * t + j - a;
-          ev_accum(unpack16(qq, j), j < jn && i >= 0 && i < n_norm, k, p1, p2, pc);
-        }
-        unsigned cc = exc[t] + pc;
-        EvPrefix e;
-        e.s1 = run.s1 + ex1[t] + p1;
-        e.s2 = run.s2 + ex2[t] + p2;
-        e.cl = run.cl + (int)(cc & 0xffffu);
-        e.ch = run.ch + (int)(cc >> 16);
-        pb[tid + 1] = e;
+      for (int j = 0; j < 7; ++j) {
+        int i = tile0 + 8 * t + j - a;
+        ev_accum(unpack16(qq, j), j < jn && i >= 0 && i < n_norm, u_lo, u_hi, pivot, p1, p2, pc);
       }
-      __syncthreads();
+      const unsigned cc = texc + pc;
+      const long long e1 = run1 + tex1 + p1;
+      const unsigned long long e2 = run2 + tex2 + p2;
+      const int el = runl + (int)(cc & 0xffffu), eh = runh + (int)(cc >> 16);
+      // prefix at the previous boundary: lane - 1, or the carry for lane 0
+      long long b1 = __shfl_up_sync(0xffffffffu, e1, 1);
+      unsigned long long b2 = __shfl_up_sync(0xffffffffu, e2, 1);
+      int bl = __shfl_up_sync(0xffffffffu, el, 1), bh = __shfl_up_sync(0xffffffffu, eh, 1);
+      int bpos = __shfl_up_sync(0xffffffffu, pos, 1);
+      if (lane == 0) { b1 = prev1; b2 = prev2; bl = prevl; bh = prevh; }
       if (inb && bidx >= 1) {
-        const EvPrefix e1 = pb[tid + 1], e0 = pb[tid];
         const int kbase = bidx - 1;
-        const int s_lo = segs[kbase], s_hi = segs[bidx];
+        const int s_hi = segs[bidx];
+        const int s_lo = (lane == 0) ? segs[kbase] : (kbase == 0 ? segs[0] : bpos);
         const int pos0 = (kbase == 0) ? 0 : s_lo;
         const int n = pos - pos0;
         double mean = qnan, sd = qnan;
         if (n > 0) {
-          const long long S1 = e1.s1 - e0.s1;
-          const unsigned long long S2 = e1.s2 - e0.s2;
-          const int nl = e1.cl - e0.cl, nh = e1.ch - e0.ch;
+          const long long S1 = e1 - b1;
+          const unsigned long long S2 = e2 - b2;
+          const int nl = el - bl, nh = eh - bh;
           const int nu = n - nl - nh;
-          const double dn = (double)n, dnu = (double)nu;
-          const double sum_u = ((double)S1 + c_off * dnu) / coef.scale;
+          const double dnu = (double)nu;
+          const double rn = ev_rcp((double)n);
+          const double sum_u = ((double)S1 + c_off * dnu) * inv_scale;
           const double sum_x = sum_u + (double)nl * k.below_val + (double)nh * k.above_val;
-          mean = sum_x / dn;
+          mean = sum_x * rn;
           if (p.compute_sd) {
             double ss = 0.0;
             if (nu > 0) {
-              unsigned __int128 num = (unsigned __int128)(unsigned long long)nu * S2 -
-                                      (unsigned __int128)((__int128)S1 * (__int128)S1);
-              double dnum = (double)(unsigned long long)(num >> 64) * 18446744073709551616.0 +
-                            (double)(unsigned long long)num;
-              ss = dnum / (dnu * coef.scale * coef.scale);
+              double dnum;
+              const unsigned long long aS1 = (unsigned long long)(S1 < 0 ? -S1 : S1);
+              if ((S2 >> 31) == 0ull && (aS1 >> 31) == 0ull) {
+                dnum = (double)((unsigned long long)nu * S2 - aS1 * aS1);
+              } else {
+                unsigned __int128 num = (unsigned __int128)(unsigned long long)nu * S2 -
+                                        (unsigned __int128)aS1 * (unsigned __int128)aS1;
+                dnum = (double)(unsigned long long)(num >> 64) * 18446744073709551616.0 +
+                       (double)(unsigned long long)num;
+              }
+              const double rnu = ev_rcp(dnu);
+              ss = dnum * rnu * inv_scale2;
               if (nl | nh) {
-                double du = sum_u / dnu - mean;
+                double du = sum_u * rnu - mean;
                 ss += dnu * du * du;
               }
             }
             if (nl) { double dl = k.below_val - mean; ss += (double)nl * dl * dl; }
             if (nh) { double dh = k.above_val - mean; ss += (double)nh * dh * dh; }
-            sd = sqrt(ss / dn);
+            sd = ev_sqrt(ss * rn);
           }
         }
         norm_mean[off + kbase] = mean;
@@ -376,17 +390,18 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         ev_start[off + kbase] = (uint32_t)s_lo;
         ev_length[off + kbase] = (uint32_t)(s_hi - s_lo);
       }
-      __syncthreads();
-      if (cntb > 0 && tid == 0) pb[0] = pb[cntb];
+      // carry: prefix at the last boundary resolved in this round
+      prev1 = __shfl_sync(0xffffffffu, e1, cntb - 1);
+      prev2 = __shfl_sync(0xffffffffu, e2, cntb - 1);
+      prevl = __shfl_sync(0xffffffffu, el, cntb - 1);
+      prevh = __shfl_sync(0xffffffffu, eh, cntb - 1);
       cur += cntb;
-      __syncthreads();
-      if (cntb < kEvThreads) break;
+      if (cntb < 32) break;
     }
-    // ---- advance the running prefix past this tile
-    run.s1 += tot1;
-    run.s2 += tot2;
-    run.cl += (int)(totc & 0xffffu);
-    run.ch += (int)(totc >> 16);
+    run1 += tot1;
+    run2 += tot2;
+    runl += (int)(totc & 0xffffu);
+    runh += (int)(totc >> 16);
   }
 }
 

@@ -17,7 +17,8 @@
 namespace nrq {
 
 constexpr int kSegWarps = 8;
-constexpr int kRegionCap = 512;  // region samples held in shared memory per warp (p99 of real regions ~200)
+constexpr int kRegionCap = 254;  // region samples held in shared memory per warp (p99 of real regions ~200)
+constexpr int kSegLut = 512;     // DAC codes covered by the per-warp table of normalised values
 constexpr unsigned kFull = 0xffffffffu;
 
 struct SegCtx {
@@ -35,6 +36,8 @@ struct SegCtx {
   double* buf_sm;
   double* buf_big;
   int big_cap;
+  const double* lut;  // normalised value of DAC code lut_lo + k
+  int lut_lo;
 };
 
 // extend_group, resquiggle.py:203-216
@@ -69,55 +72,83 @@ __device__ __forceinline__ int swallow_previous(SegCtx& c, int& lo, int hi, int&
   return NRQ_ST_OK;
 }
 
-// get_cpts, resquiggle.py:227-255.  1: change-points written to out[outpos..outpos+K); 0: None;
-// < 0: -status.
-__device__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos) {
-  if (c.limit >= 0 && K > c.limit) return -NRQ_ST_CPTS_LIMIT;
+// normalised value of a DAC code: shared-memory table over the codes that survive clipping, exact
+// division (the same arithmetic that filled the table) for anything outside it
+__device__ __forceinline__ double seg_x(const SegCtx& c, int v) {
+  unsigned k = (unsigned)(v - c.lut_lo);
+  return k < (unsigned)kSegLut ? c.lut[k] : norm_value(v, c.coef);
+}
+
+// running_diffs[i] = |2 cs[i+m] - cs[i] - cs[i+2m]| (:241-243) as an ordered key:
+// bits + 2 (0 = blacklisted, 1 = picked).  cs[i] lives at cs[i].
+__device__ __forceinline__ unsigned long long rd_key(const double* cs, int i, int m) {
+  double a = cs[i], bq = cs[i + m], cq = cs[i + 2 * m];
+  double rd = fabs(__dsub_rn(__dsub_rn(__dmul_rn(2.0, bq), a), cq));
+  return (unsigned long long)__double_as_longlong(rd) + 2ull;
+}
+
+// lexicographic arg-max of (key, index) over the warp; returns index + 1, or 0 if no lane has a candidate
+__device__ __forceinline__ unsigned warp_argmax(unsigned long long best, int bi) {
+  unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+  unsigned mh = __reduce_max_sync(kFull, hi);
+  bool c1 = hi == mh;
+  unsigned ml = __reduce_max_sync(kFull, c1 ? lo : 0u);
+  bool c2 = c1 && lo == ml;
+  return __reduce_max_sync(kFull, c2 ? (unsigned)(bi + 1) : 0u);
+}
+
+// greedy selection (:244-254) with the keys held in registers: lane owns i = lane + 32 e, e < E.
+// 1: K change-points written in ascending order; 0: None.
+template <int E>
+__device__ __forceinline__ int select_cpts_regs(const SegCtx& c, const double* cs, int nrd, int K, int t0,
+                                                int outpos) {
+  const int lane = (int)lane_id();
+  const int m = c.m;
+  unsigned long long key[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    int i = lane + 32 * e;
+    key[e] = i < nrd ? rd_key(cs, i, m) : 0ull;
+  }
+  for (int round = 0; round < K; ++round) {
+    unsigned long long best = 0;
+    int bi = -1;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if (key[e] >= 2ull && key[e] >= best) { best = key[e]; bi = lane + 32 * e; }
+    unsigned mi = warp_argmax(best, bi);
+    if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
+    const int p = (int)mi - 1;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {  // blacklist p-m+1 .. p+m (:249-250)
+      int i = lane + 32 * e;
+      if (i > p - m && i <= p + m) key[e] = (i == p || key[e] == 1ull) ? 1ull : 0ull;
+    }
+  }
+  // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
+  int cnt = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    bool f = key[e] == 1ull;
+    unsigned bal = __ballot_sync(kFull, f);
+    if (f) c.out[outpos + cnt + __popc(bal & ((1u << lane) - 1u))] = t0 + lane + 32 * e + m;
+    cnt += __popc(bal);
+  }
+  return 1;
+}
+
+// same, keys in memory (regions too large for registers / shared memory)
+__device__ int select_cpts_mem(const SegCtx& c, double* cs, int nrd, int K, int t0, int outpos) {
   const unsigned lane = lane_id();
   const int m = c.m;
-  const int t0 = c.t[start];
-  const int n = c.t[stop] - t0;
-  const int nrd = n - 2 * m + 1;  // len(running_diffs)
-  if (nrd <= 0) return 0;
-  double* buf = c.buf_sm;
-  if (n > kRegionCap) {
-    if (n > c.big_cap) return -NRQ_ST_REGION_TOO_LARGE;
-    buf = c.buf_big;
-  }
-  // x = normalised, clipped signal of the region; buf[j+1] = x[j], buf[0] = 0  (:237-239)
-  const int16_t* s = c.sig + t0;
-  for (int j = lane; j < n; j += 32) buf[j + 1] = norm_value((int)s[j], c.coef);
-  if (lane == 0) buf[0] = 0.0;
-  __syncwarp();
-  if (lane == 0) {  // np.cumsum: strictly left to right
-    double acc = 0.0;
-    int j = 1;
-    for (; j + 3 <= n; j += 4) {
-      double x0 = buf[j], x1 = buf[j + 1], x2 = buf[j + 2], x3 = buf[j + 3];
-      acc = __dadd_rn(acc, x0); buf[j] = acc;
-      acc = __dadd_rn(acc, x1); buf[j + 1] = acc;
-      acc = __dadd_rn(acc, x2); buf[j + 2] = acc;
-      acc = __dadd_rn(acc, x3); buf[j + 3] = acc;
-    }
-    for (; j <= n; ++j) { acc = __dadd_rn(acc, buf[j]); buf[j] = acc; }
-  }
-  __syncwarp();
-  // running_diffs[i] = |2 cs[i+m] - cs[i] - cs[i+2m]| (:241-243), stored in place as an ordered
-  // key: bits + 2 (0 = blacklisted, 1 = picked)
-  unsigned long long* key = reinterpret_cast<unsigned long long*>(buf);
+  unsigned long long* key = reinterpret_cast<unsigned long long*>(cs);
   for (int base = 0; base < nrd; base += 32) {
     int i = base + (int)lane;
-    unsigned long long k = 0;
-    if (i < nrd) {
-      double a = buf[i], bq = buf[i + m], cq = buf[i + 2 * m];
-      double rd = fabs(__dsub_rn(__dsub_rn(__dmul_rn(2.0, bq), a), cq));
-      k = (unsigned long long)__double_as_longlong(rd) + 2ull;
-    }
+    unsigned long long k = i < nrd ? rd_key(cs, i, m) : 0ull;
     __syncwarp();
     if (i < nrd) key[i] = k;
   }
   __syncwarp();
-  // greedy selection (:244-254)
   for (int round = 0; round < K; ++round) {
     unsigned long long best = 0;
     int bi = -1;
@@ -125,16 +156,11 @@ __device__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos)
       unsigned long long k = key[i];
       if (k >= 2ull && k >= best) { best = k; bi = i; }
     }
-    unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
-    unsigned mh = __reduce_max_sync(kFull, hi);
-    bool c1 = hi == mh;
-    unsigned ml = __reduce_max_sync(kFull, c1 ? lo : 0u);
-    bool c2 = c1 && lo == ml;
-    unsigned mi = __reduce_max_sync(kFull, c2 ? (unsigned)(bi + 1) : 0u);
-    if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
+    unsigned mi = warp_argmax(best, bi);
+    if (mi == 0u) return 0;
     int p = (int)mi - 1;
     if ((int)lane < 2 * m) {
-      int q = p - m + 1 + (int)lane;  // blacklist p-m+1 .. p+m (:249-250)
+      int q = p - m + 1 + (int)lane;
       if (q >= 0 && q < nrd) {
         if (q == p) key[q] = 1ull;
         else if (key[q] != 1ull) key[q] = 0ull;
@@ -142,7 +168,6 @@ __device__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos)
     }
     __syncwarp();
   }
-  // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
   int cnt = 0;
   for (int base = 0; base < nrd; base += 32) {
     int i = base + (int)lane;
@@ -154,8 +179,58 @@ __device__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos)
   return 1;
 }
 
+// get_cpts, resquiggle.py:227-255.  1: change-points written to out[outpos..outpos+K); 0: None;
+// < 0: -status.
+__device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos) {
+  if (c.limit >= 0 && K > c.limit) return -NRQ_ST_CPTS_LIMIT;
+  const unsigned lane = lane_id();
+  const int m = c.m;
+  const int t0 = c.t[start];
+  const int n = c.t[stop] - t0;
+  const int nrd = n - 2 * m + 1;  // len(running_diffs)
+  if (nrd <= 0) return 0;
+  const int16_t* s = c.sig + t0;
+  if (n <= kRegionCap) {
+    // shared memory: buf[1] = cs[0] = 0, buf[2 + j] = x[j] then cs[j + 1]; pairs are 16-byte aligned
+    double* buf = c.buf_sm;
+    for (int j = lane; j < n; j += 32) buf[2 + j] = seg_x(c, (int)s[j]);
+    if (lane == 0) buf[1] = 0.0;
+    __syncwarp();
+    if (lane == 0) {  // np.cumsum (:239): strictly left to right
+      double acc = 0.0;
+      int j = 0;
+      for (; j + 1 < n; j += 2) {
+        double2 v = *reinterpret_cast<double2*>(buf + 2 + j);
+        acc = __dadd_rn(acc, v.x); v.x = acc;
+        acc = __dadd_rn(acc, v.y); v.y = acc;
+        *reinterpret_cast<double2*>(buf + 2 + j) = v;
+      }
+      if (j < n) buf[2 + j] = __dadd_rn(acc, buf[2 + j]);
+    }
+    __syncwarp();
+    const double* cs = buf + 1;
+    int res;
+    if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos);
+    else if (nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos);
+    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos);
+    __syncwarp();
+    return res;
+  }
+  if (n > c.big_cap) return -NRQ_ST_REGION_TOO_LARGE;
+  double* buf = c.buf_big;  // buf[0] = cs[0], buf[j + 1] = x[j] then cs[j + 1]
+  for (int j = lane; j < n; j += 32) buf[j + 1] = seg_x(c, (int)s[j]);
+  if (lane == 0) buf[0] = 0.0;
+  __syncwarp();
+  if (lane == 0) {
+    double acc = 0.0;
+    for (int j = 1; j <= n; ++j) { acc = __dadd_rn(acc, buf[j]); buf[j] = acc; }
+  }
+  __syncwarp();
+  return select_cpts_mem(c, buf, nrd, K, t0, outpos);
+}
+
 // extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
-__device__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
+__device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
   int K;
   int st = extend_group(c, lo, hi, maxend, start, stop, K);
   if (st != NRQ_ST_OK) return st;
@@ -249,7 +324,8 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
             const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
             double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
             int32_t* __restrict__ new_segs, int32_t* __restrict__ region_samples) {
-  __shared__ double region[kSegWarps][kRegionCap + 1];
+  __shared__ __align__(16) double region[kSegWarps][kRegionCap + 2];
+  __shared__ double lut[kSegWarps][kSegLut];
   const int warp = threadIdx.x >> 5;
   const unsigned lane = lane_id();
   const int gwarp = blockIdx.x * kSegWarps + warp;
@@ -273,6 +349,18 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.m = p.min_seg_len;
     c.limit = p.num_cpts_limit;
     c.buf_sm = region[warp];
+    // table of normalised values over the codes that survive clipping (or around a pivot sample)
+    c.lut = lut[warp];
+    c.lut_lo = (int)g.sig[g.n_norm / 2] - kSegLut / 2;
+    if (c.coef.clip) {
+      double e0 = c.coef.shift + c.coef.lo * c.coef.scale, e1 = c.coef.shift + c.coef.hi * c.coef.scale;
+      double lo = fmin(e0, e1), hi = fmax(e0, e1);
+      if (isfinite(lo) && isfinite(hi) && hi - lo < (double)(kSegLut - 4) && lo > -40000.0 && hi < 40000.0)
+        c.lut_lo = (int)floor(lo) - 2;
+    }
+    __syncwarp();
+    for (int k = lane; k < kSegLut; k += 32) lut[warp][k] = norm_value(c.lut_lo + k, c.coef);
+    __syncwarp();
     c.big_cap = p.big_region_cap;
     c.buf_big = big_scratch + (size_t)gwarp * (size_t)(p.big_region_cap + 1);
     int reg = 0;
