@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libnrq.so')
+LIB_PATH = os.environ.get('NRQ_LIB_PATH') or os.path.join(_HERE, 'libnrq.so')
 
 # status codes (include/nrq.h)
 ST_OK, ST_CPTS_LIMIT, ST_TIMEOUT, ST_ZERO_LEN, ST_NEG_START, ST_PAST_END, ST_SEQ_MISMATCH, \

@@ -199,6 +199,51 @@ __device__ __forceinline__ double ev_sqrt(double y) {
   return fma(fma(-s, s, y), 0.5 * r, s);
 }
 
+
+struct EvRead {       // per-read constants of the statistics
+  double c_off;       // pivot - shift
+  double inv_scale, inv_scale2;
+  double below_val, above_val;
+  const double* rcp_tab;  // 1/n for n < 64
+  int compute_sd;
+};
+
+// mean / sd of one base from its integer sums: S1 = sum d, S2 = sum d^2 over the nu unclipped samples,
+// nl / nh samples clipped to below_val / above_val
+__device__ __forceinline__ void ev_base_stats(const EvRead& R, int n, long long S1, unsigned long long S2,
+                                              int nl, int nh, double& mean, double& sd) {
+  const int nu = n - nl - nh;
+  const double dnu = (double)nu;
+  const double rn = n < 64 ? R.rcp_tab[n] : ev_rcp((double)n);
+  const double sum_u = ((double)S1 + R.c_off * dnu) * R.inv_scale;
+  double sum_x = sum_u;
+  if (nl | nh) sum_x += (double)nl * R.below_val + (double)nh * R.above_val;
+  mean = sum_x * rn;
+  if (!R.compute_sd) return;
+  double ss = 0.0;
+  if (nu > 0) {
+    double dnum;
+    const unsigned long long aS1 = (unsigned long long)(S1 < 0 ? -S1 : S1);
+    if ((S2 >> 31) == 0ull && (aS1 >> 31) == 0ull) {
+      dnum = (double)((unsigned long long)nu * S2 - aS1 * aS1);
+    } else {
+      unsigned __int128 num = (unsigned __int128)(unsigned long long)nu * S2 -
+                              (unsigned __int128)aS1 * (unsigned __int128)aS1;
+      dnum = (double)(unsigned long long)(num >> 64) * 18446744073709551616.0 +
+             (double)(unsigned long long)num;
+    }
+    const double rnu = (nl | nh) ? (nu < 64 ? R.rcp_tab[nu] : ev_rcp(dnu)) : rn;
+    ss = dnum * rnu * R.inv_scale2;
+    if (nl | nh) {
+      double du = sum_u * rnu - mean;
+      ss += dnu * du * du;
+    }
+  }
+  if (nl) { double dl = R.below_val - mean; ss += (double)nl * dl * dl; }
+  if (nh) { double dh = R.above_val - mean; ss += (double)nh * dh * dh; }
+  sd = ev_sqrt(ss * rn);
+}
+
 __device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_sample) {
   EvClass k;
   k.u_lo = -32768; k.u_hi = 32767;
@@ -228,12 +273,22 @@ __device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_s
   return k;
 }
 
-__global__ void __launch_bounds__(kEvWarps * 32)
+#ifndef NRQ_EV_MINB
+#define NRQ_EV_MINB 4
+#endif
+__global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
               const int32_t* __restrict__ new_segs, const int32_t* __restrict__ status,
               double* __restrict__ norm_mean, double* __restrict__ norm_stdev,
               uint32_t* __restrict__ ev_start, uint32_t* __restrict__ ev_length) {
-  const int r = blockIdx.x * kEvWarps + (threadIdx.x >> 5);
+  __shared__ double rcp_tab[64];
+  __shared__ __align__(16) int loc1[kEvWarps][2][32][4];       // lane-local exclusive prefixes of d
+  __shared__ __align__(16) unsigned loc2[kEvWarps][2][32][4];  // ... and of d^2
+  __shared__ __align__(16) unsigned locc[kEvWarps][2][32][4];  // ... and of the packed clip counters
+  if (threadIdx.x < 64) rcp_tab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5;
+  const int r = blockIdx.x * kEvWarps + warp;
   if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
   const int lane = (int)lane_id();
   ReadGeom g = read_geom(b, r);
@@ -245,9 +300,17 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
 
   const EvClass k = ev_classify(coef, (int)g.sig[n_norm / 2]);  // every lane: a handful of divisions
   const int u_lo = k.u_lo, u_hi = k.u_hi, pivot = k.pivot;
-  const double c_off = __dsub_rn((double)pivot, coef.shift);
-  const double inv_scale = 1.0 / coef.scale;
-  const double inv_scale2 = inv_scale * inv_scale;
+  EvRead R;
+  R.c_off = __dsub_rn((double)pivot, coef.shift);
+  R.inv_scale = 1.0 / coef.scale;
+  R.inv_scale2 = R.inv_scale * R.inv_scale;
+  R.below_val = k.below_val;
+  R.above_val = k.above_val;
+  R.rcp_tab = rcp_tab;
+  R.compute_sd = p.compute_sd;
+  // d^2 summed over one 256-sample step fits 32 bits when |d| <= 2048
+  const unsigned range = (unsigned)(u_hi - u_lo);
+  const bool narrow = coef.clip && u_hi >= u_lo && range <= 4094u;
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   // steps are laid out on 16-byte boundaries of the raw buffer: sample i sits at slot i + a
@@ -261,8 +324,130 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   int cur = 0;  // next boundary to resolve (0 .. nb)
 
   for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
-    // ---- load 8 samples, lane totals
     const int slot = tile0 + 8 * lane;
+    // ================= fast step: interior step of a read with a narrow unclipped range =================
+    if (narrow && tile0 >= a && tile0 + kSub - a <= n_norm) {
+      const int4 q = __ldg(reinterpret_cast<const int4*>(base_al + slot));
+      int l1[8];
+      unsigned l2[8];
+      int s1 = 0;
+      unsigned s2 = 0, out_of_range = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int v = unpack16(q, j);
+        const bool unc = (unsigned)(v - u_lo) <= range;
+        out_of_range |= unc ? 0u : 1u;
+        const int d = unc ? v - pivot : 0;
+        l1[j] = s1;
+        l2[j] = s2;
+        s1 += d;
+        s2 += (unsigned)(d * d);
+      }
+      *reinterpret_cast<int4*>(loc1[warp][0][lane]) = make_int4(l1[0], l1[1], l1[2], l1[3]);
+      *reinterpret_cast<int4*>(loc1[warp][1][lane]) = make_int4(l1[4], l1[5], l1[6], l1[7]);
+      *reinterpret_cast<uint4*>(loc2[warp][0][lane]) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
+      *reinterpret_cast<uint4*>(loc2[warp][1][lane]) = make_uint4(l2[4], l2[5], l2[6], l2[7]);
+      // clipped samples are rare: only steps that contain one carry the (below, above) counters
+      const bool anyc = __any_sync(0xffffffffu, out_of_range);
+      unsigned cnt = 0;
+      if (anyc) {
+        unsigned lc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int v = unpack16(q, j);
+          lc[j] = cnt;
+          cnt += (v < u_lo ? 1u : 0u) + (v > u_hi ? 65536u : 0u);
+        }
+        *reinterpret_cast<uint4*>(locc[warp][0][lane]) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
+        *reinterpret_cast<uint4*>(locc[warp][1][lane]) = make_uint4(lc[4], lc[5], lc[6], lc[7]);
+      }
+      int i1 = s1;
+      unsigned i2 = s2, ic = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t1 = __shfl_up_sync(0xffffffffu, i1, o);
+        unsigned t2 = __shfl_up_sync(0xffffffffu, i2, o);
+        if (lane >= o) { i1 += t1; i2 += t2; }
+        if (anyc) {
+          unsigned tc = __shfl_up_sync(0xffffffffu, ic, o);
+          if (lane >= o) ic += tc;
+        }
+      }
+      const int ex1 = i1 - s1;
+      const unsigned ex2 = i2 - s2, exc = ic - cnt;
+      const int tot1 = __shfl_sync(0xffffffffu, i1, 31);
+      const unsigned tot2 = __shfl_sync(0xffffffffu, i2, 31);
+      const unsigned totc = anyc ? __shfl_sync(0xffffffffu, ic, 31) : 0u;
+      __syncwarp();
+      const int tile_end = tile0 + kSub;
+      for (;;) {
+        const int bidx = cur + lane;
+        int pos = 0;
+        bool inb = false;
+        if (bidx <= nb) {
+          pos = (bidx == 0) ? 0 : (bidx == nb ? n_norm : segs[bidx]);
+          inb = pos + a < tile_end;
+        }
+        const unsigned bal = __ballot_sync(0xffffffffu, inb);
+        const int cntb = __popc(bal);
+        if (cntb == 0) break;
+        const int sl = inb ? pos + a - tile0 : 0;
+        const int t = sl >> 3, jj = sl & 7;
+        const int E1 = __shfl_sync(0xffffffffu, ex1, t) + loc1[warp][jj >> 2][t][jj & 3];
+        const unsigned E2 = __shfl_sync(0xffffffffu, ex2, t) + loc2[warp][jj >> 2][t][jj & 3];
+        const int pE1 = __shfl_up_sync(0xffffffffu, E1, 1);
+        const unsigned pE2 = __shfl_up_sync(0xffffffffu, E2, 1);
+        const int bpos = __shfl_up_sync(0xffffffffu, pos, 1);
+        int el = runl, eh = runh, pl = runl, ph = runh;
+        if (anyc) {
+          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][jj >> 2][t][jj & 3];
+          el += (int)(EC & 0xffffu);
+          eh += (int)(EC >> 16);
+          pl = __shfl_up_sync(0xffffffffu, el, 1);
+          ph = __shfl_up_sync(0xffffffffu, eh, 1);
+        }
+        if (inb && bidx >= 1) {
+          const int kbase = bidx - 1;
+          const int s_hi = segs[bidx];
+          const int s_lo = (lane == 0) ? segs[kbase] : (kbase == 0 ? segs[0] : bpos);
+          const int pos0 = (kbase == 0) ? 0 : s_lo;
+          const int n = pos - pos0;
+          double mean = qnan, sd = qnan;
+          if (n > 0) {
+            long long S1;
+            unsigned long long S2;
+            if (lane == 0) {  // the base may have begun in an earlier step
+              S1 = run1 + E1 - prev1;
+              S2 = run2 + E2 - prev2;
+              pl = prevl;
+              ph = prevh;
+            } else {
+              S1 = (long long)(E1 - pE1);
+              S2 = (unsigned long long)(E2 - pE2);
+            }
+            ev_base_stats(R, n, S1, S2, el - pl, eh - ph, mean, sd);
+          }
+          norm_mean[off + kbase] = mean;
+          norm_stdev[off + kbase] = sd;
+          ev_start[off + kbase] = (uint32_t)s_lo;
+          ev_length[off + kbase] = (uint32_t)(s_hi - s_lo);
+        }
+        prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
+        prev2 = run2 + __shfl_sync(0xffffffffu, E2, cntb - 1);
+        prevl = anyc ? __shfl_sync(0xffffffffu, el, cntb - 1) : runl;
+        prevh = anyc ? __shfl_sync(0xffffffffu, eh, cntb - 1) : runh;
+        cur += cntb;
+        if (cntb < 32) break;
+      }
+      run1 += tot1;
+      run2 += tot2;
+      runl += (int)(totc & 0xffffu);
+      runh += (int)(totc >> 16);
+      __syncwarp();
+      continue;
+    }
+    // ================= general step =================
+    // ---- load 8 samples, lane totals
     int4 q = make_int4(0, 0, 0, 0);
     if (slot < n_norm + a) {
       const int16_t* ptr = base_al + slot;
@@ -350,41 +535,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         const int pos0 = (kbase == 0) ? 0 : s_lo;
         const int n = pos - pos0;
         double mean = qnan, sd = qnan;
-        if (n > 0) {
-          const long long S1 = e1 - b1;
-          const unsigned long long S2 = e2 - b2;
-          const int nl = el - bl, nh = eh - bh;
-          const int nu = n - nl - nh;
-          const double dnu = (double)nu;
-          const double rn = ev_rcp((double)n);
-          const double sum_u = ((double)S1 + c_off * dnu) * inv_scale;
-          const double sum_x = sum_u + (double)nl * k.below_val + (double)nh * k.above_val;
-          mean = sum_x * rn;
-          if (p.compute_sd) {
-            double ss = 0.0;
-            if (nu > 0) {
-              double dnum;
-              const unsigned long long aS1 = (unsigned long long)(S1 < 0 ? -S1 : S1);
-              if ((S2 >> 31) == 0ull && (aS1 >> 31) == 0ull) {
-                dnum = (double)((unsigned long long)nu * S2 - aS1 * aS1);
-              } else {
-                unsigned __int128 num = (unsigned __int128)(unsigned long long)nu * S2 -
-                                        (unsigned __int128)aS1 * (unsigned __int128)aS1;
-                dnum = (double)(unsigned long long)(num >> 64) * 18446744073709551616.0 +
-                       (double)(unsigned long long)num;
-              }
-              const double rnu = ev_rcp(dnu);
-              ss = dnum * rnu * inv_scale2;
-              if (nl | nh) {
-                double du = sum_u * rnu - mean;
-                ss += dnu * du * du;
-              }
-            }
-            if (nl) { double dl = k.below_val - mean; ss += (double)nl * dl * dl; }
-            if (nh) { double dh = k.above_val - mean; ss += (double)nh * dh * dh; }
-            sd = ev_sqrt(ss * rn);
-          }
-        }
+        if (n > 0) ev_base_stats(R, n, e1 - b1, e2 - b2, el - bl, eh - bh, mean, sd);
         norm_mean[off + kbase] = mean;
         norm_stdev[off + kbase] = sd;
         ev_start[off + kbase] = (uint32_t)s_lo;

@@ -104,32 +104,36 @@ __device__ __forceinline__ int select_cpts_regs(const SegCtx& c, const double* c
                                                 int outpos) {
   const int lane = (int)lane_id();
   const int m = c.m;
-  unsigned long long key[E];
+  unsigned long long key[E];  // bits(rd) + 1 while the position is still a candidate, 0 once it is not
+  unsigned picked = 0;        // bit e: position lane + 32 e was chosen
 #pragma unroll
   for (int e = 0; e < E; ++e) {
     int i = lane + 32 * e;
-    key[e] = i < nrd ? rd_key(cs, i, m) : 0ull;
+    key[e] = i < nrd ? rd_key(cs, i, m) - 1ull : 0ull;
   }
   for (int round = 0; round < K; ++round) {
     unsigned long long best = 0;
     int bi = -1;
 #pragma unroll
-    for (int e = 0; e < E; ++e)
-      if (key[e] >= 2ull && key[e] >= best) { best = key[e]; bi = lane + 32 * e; }
+    for (int e = E - 1; e >= 0; --e)  // descending + strict: the larger index wins ties
+      if (key[e] > best) { best = key[e]; bi = lane + 32 * e; }
     unsigned mi = warp_argmax(best, bi);
     if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
     const int p = (int)mi - 1;
 #pragma unroll
     for (int e = 0; e < E; ++e) {  // blacklist p-m+1 .. p+m (:249-250)
       int i = lane + 32 * e;
-      if (i > p - m && i <= p + m) key[e] = (i == p || key[e] == 1ull) ? 1ull : 0ull;
+      if ((unsigned)(i - (p - m + 1)) < (unsigned)(2 * m)) {
+        key[e] = 0ull;
+        if (i == p) picked |= 1u << e;
+      }
     }
   }
   // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
   int cnt = 0;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    bool f = key[e] == 1ull;
+    bool f = (picked >> e) & 1u;
     unsigned bal = __ballot_sync(kFull, f);
     if (f) c.out[outpos + cnt + __popc(bal & ((1u << lane) - 1u))] = t0 + lane + 32 * e + m;
     cnt += __popc(bal);
@@ -199,6 +203,19 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, in
     if (lane == 0) {  // np.cumsum (:239): strictly left to right
       double acc = 0.0;
       int j = 0;
+      for (; j + 7 < n; j += 8) {
+        double2* q = reinterpret_cast<double2*>(buf + 2 + j);
+        double2 v0 = q[0], v1 = q[1], v2 = q[2], v3 = q[3];
+        acc = __dadd_rn(acc, v0.x); v0.x = acc;
+        acc = __dadd_rn(acc, v0.y); v0.y = acc;
+        acc = __dadd_rn(acc, v1.x); v1.x = acc;
+        acc = __dadd_rn(acc, v1.y); v1.y = acc;
+        acc = __dadd_rn(acc, v2.x); v2.x = acc;
+        acc = __dadd_rn(acc, v2.y); v2.y = acc;
+        acc = __dadd_rn(acc, v3.x); v3.x = acc;
+        acc = __dadd_rn(acc, v3.y); v3.y = acc;
+        q[0] = v0; q[1] = v1; q[2] = v2; q[3] = v3;
+      }
       for (; j + 1 < n; j += 2) {
         double2 v = *reinterpret_cast<double2*>(buf + 2 + j);
         acc = __dadd_rn(acc, v.x); v.x = acc;
@@ -262,9 +279,11 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
   if (c.n_ind > 0) {
     int lo = 0, hi = 0, maxend = c.ind[0].y;
     int start, stop;
+    int4 ahead = c.n_ind > 1 ? c.ind[1] : make_int4(0, 0, 0, 0);
     for (int k = 1; k < c.n_ind; ++k) {
       if (timeout_ns > 0 && global_ns() - t_begin > timeout_ns) return NRQ_ST_TIMEOUT;  // :288-289
-      int4 nxt = c.ind[k];
+      const int4 nxt = ahead;
+      if (k + 1 < c.n_ind) ahead = c.ind[k + 1];
       if (maxend >= nxt.x) {  // :291-292
         hi = k;
         maxend = max(maxend, nxt.y);
@@ -319,7 +338,10 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
   return NRQ_ST_OK;
 }
 
-__global__ void __launch_bounds__(kSegWarps * 32)
+#ifndef NRQ_SEG_MINB
+#define NRQ_SEG_MINB 4
+#endif
+__global__ void __launch_bounds__(kSegWarps * 32, NRQ_SEG_MINB)
 k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int64_t* __restrict__ indel_off,
             const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
             double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
