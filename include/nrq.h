@@ -94,6 +94,12 @@ typedef struct nrq_batch {
   const uint8_t* genome_align;
   const int64_t* align_off;
   const double*  scale_values_in;
+  /* Optional: an already normalised float64 signal per read (norm_off[R+1] offsets).  When non-NULL,
+   * nrq_resegment and the exact event-table kernel read it instead of normalising `raw`: this is how the
+   * reference's get_indel_groups(alignVals, align_segs, raw_signal, ...) call surface (resquiggle.py:139-141),
+   * which receives the normalised signal, is served.  NULL in the batch pipeline. */
+  const double*  norm_signal;
+  const int64_t* norm_off;
 } nrq_batch;
 
 /* Outputs (device).  Event table columns are the fields of the reference's
@@ -141,12 +147,14 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
                          const int64_t* norm_off, double* norm_signal, void* stream);
 
 /* a3-a6: get_indel_groups + splice (resquiggle.py:203-316, 362-387) -> new_segs, status.
- * group_scratch: int32[4*indel_capacity]; big_scratch: see nrq_workspace_bytes; region_samples may be NULL. */
+ * group_scratch: int32[4*indel_capacity]; big_scratch: see nrq_workspace_bytes; region_samples and n_groups may be NULL.
+ * On return group_scratch holds, per read at int4 index indel_off[r], n_groups[r] records
+ * (group_start, group_stop, first indel index, max indel end) = the reference's indelGroupStats. */
 int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                   const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
                   int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
                   int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
-                  void* stream);
+                  int32_t* n_groups, void* stream);
 
 /* a7: per-base mean / sd / start / length / base (resquiggle.py:60-70). */
 int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale_values,

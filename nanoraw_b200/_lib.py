@@ -26,7 +26,7 @@ class NrqBatch(C.Structure):
         ('n_reads', C.c_int32), ('raw', C.c_void_p), ('raw_off', C.c_void_p),
         ('read_start', C.c_void_p), ('starts', C.c_void_p), ('starts_off', C.c_void_p),
         ('read_align', C.c_void_p), ('genome_align', C.c_void_p), ('align_off', C.c_void_p),
-        ('scale_values_in', C.c_void_p)]
+        ('scale_values_in', C.c_void_p), ('norm_signal', C.c_void_p), ('norm_off', C.c_void_p)]
 
 
 class NrqResults(C.Structure):
@@ -48,7 +48,7 @@ SYMBOLS = {
     'nrq_norm_stats': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P]),
     'nrq_normalize_signal': (C.c_int, [C.POINTER(NrqBatch), _P, _P, _P, _P, _P]),
     'nrq_resegment': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
-                                C.c_int64, _P, _P, _P, _P, _P]),
+                                C.c_int64, _P, _P, _P, _P, _P, _P]),
     'nrq_event_table': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P]),
     'nrq_resquiggle_batch': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams),

@@ -13,7 +13,7 @@ class ReadBatch(object):
               'read_align', 'genome_align', 'align_off')
 
     def __init__(self, raw, raw_off, read_start, starts, starts_off, read_align,
-                 genome_align, align_off, scale_values_in=None):
+                 genome_align, align_off, scale_values_in=None, norm_signal=None, norm_off=None):
         self.raw = raw
         self.raw_off = raw_off
         self.read_start = read_start
@@ -23,6 +23,9 @@ class ReadBatch(object):
         self.genome_align = genome_align
         self.align_off = align_off
         self.scale_values_in = scale_values_in
+        # optional pre-normalised float64 signal (get_indel_groups call surface)
+        self.norm_signal = norm_signal
+        self.norm_off = norm_off
 
     @property
     def n_reads(self):

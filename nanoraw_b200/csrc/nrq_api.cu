@@ -185,7 +185,7 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
                   const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
                   int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
                   int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
-                  void* stream) {
+                  int32_t* n_groups, void* stream) {
   if (int e = check_batch(b)) return e;
   if (int e = check_params(p)) return e;
   if (!scale_values || !indel_off || !indels || !n_bases || !group_scratch || !work_counter || !status ||
@@ -201,7 +201,8 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
   if (e != cudaSuccess) return fail("memset work_counter", e);
   nrq::k_resegment<<<grid, nrq::kSegWarps * 32, 0, s>>>(
       *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), n_bases,
-      reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs, region_samples);
+      reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs, region_samples,
+      n_groups);
   NRQ_CHECK_LAUNCH("k_resegment");
   return 0;
 }
@@ -216,7 +217,7 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
     return fail("nrq_event_table: NULL argument");
   (void)ev_base;  // written by nrq_find_indels
   if (b->n_reads == 0) return 0;
-  if (p->debug_flags & 2)
+  if ((p->debug_flags & 2) || b->norm_signal)
     nrq::k_event_table_exact<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   else
@@ -254,7 +255,7 @@ static int resquiggle_batch_impl(const nrq_batch* b, const nrq_params* p, const 
   if (int e = nrq_norm_stats(b, p, out->status, out->scale_values, stream)) return e;
   mark(2);
   if (int e = nrq_resegment(b, p, out->scale_values, w.indel_off, w.indels, out->n_bases, w.groups, w.big,
-                            w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, stream))
+                            w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, nullptr, stream))
     return e;
   mark(3);
   if (int e = nrq_event_table(b, p, out->scale_values, out->n_bases, out->new_segs, out->status, out->norm_mean,
@@ -348,6 +349,8 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     return d;
   };
   nrq_batch d = *b;
+  d.norm_signal = nullptr;  // the host entry point always normalises from raw
+  d.norm_off = nullptr;
   d.raw = (const int16_t*)up(b->raw, 2 * (size_t)n_raw);
   d.raw_off = (const int64_t*)up(b->raw_off, 8 * (size_t)(R + 1));
   d.read_start = (const int32_t*)up(b->read_start, 4 * (size_t)R);

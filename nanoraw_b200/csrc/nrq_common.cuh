@@ -39,6 +39,7 @@ struct ReadGeom {
   int n_starts;         // Br + 1
   int n_obs;            // starts[-1] = read_obs_len
   int n_norm;           // len(norm_signal) = min(n_obs, samples available)
+  const double* xsig;   // pre-normalised float64 signal (nrq_batch.norm_signal) or nullptr
 };
 
 __device__ __forceinline__ ReadGeom read_geom(const nrq_batch& b, int r) {
@@ -53,5 +54,10 @@ __device__ __forceinline__ ReadGeom read_geom(const nrq_batch& b, int r) {
   int64_t avail = (r1 - r0) - rs;
   if (avail < 0) avail = 0;
   g.n_norm = (int)(g.n_obs < avail ? g.n_obs : avail);
+  g.xsig = nullptr;
+  if (b.norm_signal) {
+    g.xsig = b.norm_signal + b.norm_off[r];
+    g.n_norm = (int)(b.norm_off[r + 1] - b.norm_off[r]);
+  }
   return g;
 }

@@ -21,10 +21,12 @@ constexpr int kLut = 1024;
 
 struct XAt {
   const int16_t* sig;
+  const double* xsig;  // pre-normalised signal or nullptr
   const double* lut;
   int lut_lo;
   NormCoef coef;
   __device__ __forceinline__ double operator()(int i) const {
+    if (xsig) return xsig[i];
     int v = (int)sig[i];
     unsigned k = (unsigned)(v - lut_lo);
     return k < (unsigned)kLut ? lut[k] : norm_value(v, coef);
@@ -113,7 +115,7 @@ k_event_table_exact(nrq_batch b, nrq_params p, const double* __restrict__ sv, co
   const size_t off = (size_t)b.align_off[r];
 
   // table of normalised values over the codes that survive clipping (or around a pivot sample)
-  int lut_lo = (int)g.sig[g.n_norm / 2] - kLut / 2;
+  int lut_lo = (g.xsig ? 0 : (int)g.sig[g.n_norm / 2]) - kLut / 2;
   if (coef.clip) {
     double a = coef.shift + coef.lo * coef.scale, c = coef.shift + coef.hi * coef.scale;
     double lo = fmin(a, c), hi = fmax(a, c);
@@ -123,7 +125,7 @@ k_event_table_exact(nrq_batch b, nrq_params p, const double* __restrict__ sv, co
   for (int k = tid; k < kLut; k += kEvThreads) lut[k] = norm_value(lut_lo + k, coef);
   __syncthreads();
 
-  XAt x{g.sig, lut, lut_lo, coef};
+  XAt x{g.sig, g.xsig, lut, lut_lo, coef};
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
   for (int bi = tid; bi < nb; bi += kEvThreads) {
     int s_lo = segs[bi], s_hi = segs[bi + 1];

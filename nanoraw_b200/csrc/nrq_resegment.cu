@@ -25,6 +25,7 @@ struct SegCtx {
   const int32_t* t;   // starts_rel_to_read
   int last;           // Br (largest index into t)
   const int16_t* sig;
+  const double* xsig;  // pre-normalised signal (API-compat path) or nullptr
   NormCoef coef;
   const int4* ind;    // (start, end, diff, diff_prefix)
   int n_ind;
@@ -197,7 +198,8 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, in
   if (n <= kRegionCap) {
     // shared memory: buf[1] = cs[0] = 0, buf[2 + j] = x[j] then cs[j + 1]; pairs are 16-byte aligned
     double* buf = c.buf_sm;
-    for (int j = lane; j < n; j += 32) buf[2 + j] = seg_x(c, (int)s[j]);
+    if (c.xsig) for (int j = lane; j < n; j += 32) buf[2 + j] = c.xsig[t0 + j];
+    else for (int j = lane; j < n; j += 32) buf[2 + j] = seg_x(c, (int)s[j]);
     if (lane == 0) buf[1] = 0.0;
     __syncwarp();
     if (lane == 0) {  // np.cumsum (:239): strictly left to right
@@ -235,7 +237,8 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, in
   }
   if (n > c.big_cap) return -NRQ_ST_REGION_TOO_LARGE;
   double* buf = c.buf_big;  // buf[0] = cs[0], buf[j + 1] = x[j] then cs[j + 1]
-  for (int j = lane; j < n; j += 32) buf[j + 1] = seg_x(c, (int)s[j]);
+  if (c.xsig) for (int j = lane; j < n; j += 32) buf[j + 1] = c.xsig[t0 + j];
+  else for (int j = lane; j < n; j += 32) buf[j + 1] = seg_x(c, (int)s[j]);
   if (lane == 0) buf[0] = 0.0;
   __syncwarp();
   if (lane == 0) {
@@ -345,7 +348,8 @@ __global__ void __launch_bounds__(kSegWarps * 32, NRQ_SEG_MINB)
 k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int64_t* __restrict__ indel_off,
             const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
             double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
-            int32_t* __restrict__ new_segs, int32_t* __restrict__ region_samples) {
+            int32_t* __restrict__ new_segs, int32_t* __restrict__ region_samples,
+            int32_t* __restrict__ n_groups) {
   __shared__ __align__(16) double region[kSegWarps][kRegionCap + 2];
   __shared__ double lut[kSegWarps][kSegLut];
   const int warp = threadIdx.x >> 5;
@@ -362,6 +366,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.t = g.starts;
     c.last = g.n_starts - 1;
     c.sig = g.sig;
+    c.xsig = g.xsig;
     c.coef = load_coef(sv, r);
     c.ind = indels + indel_off[r];
     c.n_ind = (int)(indel_off[r + 1] - indel_off[r]);
@@ -373,7 +378,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.buf_sm = region[warp];
     // table of normalised values over the codes that survive clipping (or around a pivot sample)
     c.lut = lut[warp];
-    c.lut_lo = (int)g.sig[g.n_norm / 2] - kSegLut / 2;
+    c.lut_lo = (g.xsig ? 0 : (int)g.sig[g.n_norm / 2]) - kSegLut / 2;
     if (c.coef.clip) {
       double e0 = c.coef.shift + c.coef.lo * c.coef.scale, e1 = c.coef.shift + c.coef.hi * c.coef.scale;
       double lo = fmin(e0, e1), hi = fmax(e0, e1);
@@ -389,6 +394,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     int st = resegment_read(c, p.timeout_ns, n_bases[r], g.n_norm, reg);
     if (lane == 0 && st != NRQ_ST_OK) status[r] = st;
     if (lane == 0 && region_samples) region_samples[r] = reg;
+    if (lane == 0 && n_groups) n_groups[r] = c.ng;
     __syncwarp();
   }
 }

@@ -52,6 +52,7 @@ def _ptr(t):
 
 class DeviceBatch(object):
     """A ReadBatch resident in HBM (torch tensors) plus the nrq_batch struct pointing at it."""
+    OPTIONAL = ('scale_values_in', 'norm_signal', 'norm_off')
 
     def __init__(self, batch: ReadBatch, device, non_blocking=False, pin=False):
         import torch
@@ -60,8 +61,8 @@ class DeviceBatch(object):
         self.device = device
         self.host = batch
         self.t = {}
-        for name in ReadBatch.FIELDS + ('scale_values_in',):
-            arr = getattr(batch, name)
+        for name in ReadBatch.FIELDS + self.OPTIONAL:
+            arr = getattr(batch, name, None)
             if arr is None:
                 self.t[name] = None
                 continue
@@ -79,14 +80,14 @@ class DeviceBatch(object):
         self.total_align = total_align
         self.device = device
         self.host = host
-        self.t = {name: tensors.get(name) for name in ReadBatch.FIELDS + ('scale_values_in',)}
+        self.t = {name: tensors.get(name) for name in ReadBatch.FIELDS + self.OPTIONAL}
         self.c = self._struct()
         return self
 
     def _struct(self):
         b = _lib.NrqBatch()
         b.n_reads = self.n_reads
-        for name in ReadBatch.FIELDS + ('scale_values_in',):
+        for name in ReadBatch.FIELDS + self.OPTIONAL:
             setattr(b, name, _ptr(self.t[name]))
         return b
 
@@ -300,3 +301,92 @@ class ResquiggleEngine(object):
         sigs = [h[off[r]:off[r] + min(int(n_samp[r]), max(int(raw_len[r]), 0))]
                 for r in range(dbatch.n_reads)]
         return st, svh, sigs
+
+    def indel_groups(self, read_align, genome_align, align_segs, norm_signal, min_seg_len=4,
+                     timeout=None, num_cpts_limit=None):
+        """get_indel_groups (resquiggle.py:139-316) for ONE read whose normalised float64 signal is
+        given.  -> (status, [(group_start, group_stop, cpts, indels)]) with indels as (start, end, diff)."""
+        t = self.torch
+        sig = np.ascontiguousarray(norm_signal, dtype=np.float64)
+        batch = ReadBatch.from_arrays([np.zeros(1, np.int16)], [0], [align_segs], [read_align],
+                                      [genome_align])
+        batch.norm_signal = sig
+        batch.norm_off = np.array([0, len(sig)], dtype=np.int64)
+        db = self.upload(batch)
+        status, n_ind, n_bases, off, indels, _ = self.find_indels(db)
+        params = ResquiggleParams(num_cpts_limit=num_cpts_limit, timeout=timeout,
+                                  min_event_obs=min_seg_len, outlier_thresh=None)
+        pc = params.to_c()
+        total = max(int(off[-1]), 1)
+        with t.cuda.device(self.device):
+            d_status = t.from_numpy(status.copy()).to(self.device)
+            d_off = t.from_numpy(off).to(self.device)
+            d_ind = t.from_numpy(np.ascontiguousarray(indels.reshape(-1))).to(self.device) \
+                if len(indels) else t.zeros(4, dtype=t.int32, device=self.device)
+            d_nb = t.from_numpy(n_bases).to(self.device)
+            groups = t.zeros(4 * total, dtype=t.int32, device=self.device)
+            ws = self.workspace(1, batch.total_align, pc)
+            big = t.empty(ws.numel() // 8, dtype=t.float64, device=self.device)
+            counter = t.zeros(8, dtype=t.int32, device=self.device)
+            sv = t.tensor([0.0, 1.0, float('nan'), float('nan')], dtype=t.float64, device=self.device)
+            segs = t.zeros(batch.total_align + 2, dtype=t.int32, device=self.device)
+            ng = t.zeros(1, dtype=t.int32, device=self.device)
+            rc = self.lib.nrq_resegment(
+                C.byref(db.c), C.byref(pc), _ptr(sv), _ptr(d_off), _ptr(d_ind), _ptr(d_nb), _ptr(groups),
+                _ptr(big), big.numel(), _ptr(counter), _ptr(d_status), _ptr(segs), C.c_void_p(0), _ptr(ng),
+                self._stream())
+            _lib.check(rc, 'nrq_resegment')
+        st = int(d_status.cpu()[0])
+        out = []
+        if st == _lib.ST_OK:
+            g = groups.cpu().numpy().reshape(-1, 4)[:int(ng.cpu()[0])]
+            new_segs = segs.cpu().numpy()
+            dpre = indels[:, 3] if len(indels) else np.zeros(0, np.int32)
+            for gi, (g_start, g_stop, lo, _maxend) in enumerate(g):
+                hi = int(g[gi + 1][2]) if gi + 1 < len(g) else len(indels)
+                grp = indels[lo:hi]
+                k = int(grp[:, 2].sum()) + g_stop - g_start - 1
+                first = g_start + int(dpre[lo]) + 1
+                out.append((int(g_start), int(g_stop), new_segs[first:first + k].astype(np.int64).tolist(),
+                            [tuple(int(v) for v in row[:3]) for row in grp]))
+        return st, out
+
+    def event_stats(self, norm_signal, new_segs, compute_sd=True):
+        """per-base mean / sd of an already normalised signal (resquiggle.py:62-64), numpy summation
+        order, for ONE read.  -> (norm_mean, norm_stdev)."""
+        t = self.torch
+        sig = np.ascontiguousarray(norm_signal, dtype=np.float64)
+        new_segs = np.asarray(new_segs)
+        nb = len(new_segs) - 1
+        dummy = np.full(max(nb, 1), ord('A'), dtype=np.uint8)
+        batch = ReadBatch.from_arrays([np.zeros(1, np.int16)], [0], [np.array([0, len(sig)])], [dummy], [dummy])
+        batch.norm_signal = sig
+        batch.norm_off = np.array([0, len(sig)], dtype=np.int64)
+        db = self.upload(batch)
+        pc = ResquiggleParams(compute_sd=compute_sd, exact_stats=True, outlier_thresh=None).to_c()
+        with t.cuda.device(self.device):
+            sv = t.tensor([0.0, 1.0, float('nan'), float('nan')], dtype=t.float64, device=self.device)
+            d_nb = t.tensor([nb], dtype=t.int32, device=self.device)
+            d_segs = t.from_numpy(new_segs.astype(np.int32)).to(self.device)
+            d_status = t.zeros(1, dtype=t.int32, device=self.device)
+            mean = t.empty(max(nb, 1), dtype=t.float64, device=self.device)
+            sd = t.empty(max(nb, 1), dtype=t.float64, device=self.device)
+            st = t.empty(max(nb, 1), dtype=t.int32, device=self.device)
+            ln = t.empty(max(nb, 1), dtype=t.int32, device=self.device)
+            rc = self.lib.nrq_event_table(C.byref(db.c), C.byref(pc), _ptr(sv), _ptr(d_nb), _ptr(d_segs),
+                                          _ptr(d_status), _ptr(mean), _ptr(sd), _ptr(st), _ptr(ln),
+                                          C.c_void_p(0), self._stream())
+            _lib.check(rc, 'nrq_event_table')
+        return mean.cpu().numpy()[:nb], sd.cpu().numpy()[:nb]
+
+
+_ENGINE = {}
+
+
+def get_engine(device=None):
+    """process-wide engine per device (created on first use; raises without a GPU / libnrq.so)"""
+    import torch
+    key = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
+    if key not in _ENGINE:
+        _ENGINE[key] = ResquiggleEngine(device)
+    return _ENGINE[key]

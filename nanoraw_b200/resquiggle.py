@@ -1,0 +1,318 @@
+"""Host side of the re-squiggle hot path: the call surface of nanoraw/resquiggle.py:55-440.
+
+Same names, argument order and meaning, error strings, queue items and RawGenomeCorrected
+FAST5 layout as the reference (lines cited per function).  What changes is the body of the
+re-squiggle worker: instead of one numpy pass per read it packs the reads it dequeues into
+ragged CSR batches, runs them through libnrq's CUDA kernels (nanoraw_b200.engine) and scatters
+the per-read results to the FAST5 writer.  Per-read failures come back as status codes and are
+turned into the exceptions / strings the reference produces (nanoraw_b200.errors).  There is
+no CPU implementation of the signal path: without a GPU these functions fail loudly.
+
+The front end (FAST5 events, SAM parsing, mapper call) lives in nanoraw_b200.frontend and the
+orchestration / CLI entry in nanoraw_b200.pipeline; their public names are re-exported here so
+that `resquiggle.<name>` resolves as it does in the reference.  The reference's unused m5
+parser (resquiggle.py:496-581, dead code: the output format is always 'sam', :706) is not
+reproduced.
+"""
+import os
+import queue
+import sys
+from collections import namedtuple
+
+import numpy as np
+
+from . import fast5_io
+from . import messages as msg
+from . import nanoraw_helper as nh
+from .errors import exception_for
+from .frontend import (  # noqa: F401  (re-exported call surface)
+    SAM_FIELDS, align_and_parse, align_reads, align_to_genome, alignment_worker,
+    fix_all_clipped_bases, fix_raw_starts_for_clipped_bases, fix_stay_states, genomeLoc,
+    get_read_data, parse_sam_output, parse_sam_record, prep_bwa_mem_options, prep_fast5,
+    prep_graphmap_options, readInfo)
+
+VERBOSE = False
+
+# reads per device batch in the re-squiggle worker (additive knob, not a reference option)
+DEVICE_BATCH_READS = int(os.environ.get('NANORAW_B200_BATCH_READS', '512'))
+
+indelStats = namedtuple('indelStats', ('start', 'end', 'diff'))  # :29-30
+indelGroupStats = namedtuple('indelGroupStats', ('start', 'end', 'cpts', 'indels'))  # :31-32
+
+EVENT_DTYPE = [('norm_mean', '<f8'), ('norm_stdev', '<f8'),
+               ('start', '<u4'), ('length', '<u4'), ('base', 'S1')]  # :69-70
+
+
+
+def _rows(alignVals):
+    """alignVals -> (read row, genome row) as str.  Accepts the reference's list of
+    (read_base, genome_base) pairs or an already split (read_align, genome_align) tuple."""
+    if isinstance(alignVals, tuple) and len(alignVals) == 2 and not isinstance(alignVals[0], tuple):
+        ra, ga = alignVals
+        if isinstance(ra, bytes):
+            ra, ga = ra.decode(), ga.decode()
+        return ra, ga
+    return ''.join(r for r, _ in alignVals), ''.join(g for _, g in alignVals)
+
+
+#################################################
+########## Raw Signal Re-squiggle Code ##########
+#################################################
+
+def write_new_fast5_group(
+        filename, genome_location, read_info,
+        read_start_rel_to_raw, new_segs, align_seq, alignVals,
+        old_segs, norm_signal, scale_values, corrected_group,
+        basecall_subgroup, norm_type, outlier_thresh, compute_sd, event_data=None):
+    """resquiggle.py:55-137.  `event_data` (additive) lets the batch worker hand over the event
+    table the device already produced; when absent the per-base statistics of `norm_signal` are
+    computed on the GPU (nrq_event_table, numpy summation order)."""
+    read_align, genome_align = _rows(alignVals)
+    try:
+        if event_data is None:
+            from .engine import get_engine
+            means, sds = get_engine().event_stats(norm_signal, new_segs, compute_sd)
+            event_data = np.empty(len(new_segs) - 1, dtype=EVENT_DTYPE)
+            event_data['norm_mean'] = means
+            event_data['norm_stdev'] = sds
+            event_data['start'] = new_segs[:-1]
+            event_data['length'] = np.diff(new_segs)
+            event_data['base'] = np.frombuffer(align_seq.encode(), dtype='S1')
+        np_read_align = np.frombuffer(read_align.encode(), dtype='S1')
+        np_genome_align = np.frombuffer(genome_align.encode(), dtype='S1')
+    except Exception:
+        raise NotImplementedError(msg.EVENTS)
+
+    try:
+        read_data = fast5_io.open_fast5(filename, 'r+')
+    except Exception:
+        raise NotImplementedError(msg.OPEN_FOR_WRITE)
+
+    # layout: docs/resquiggle.rst:11-55, resquiggle.py:89-124
+    subgroup_attrs = (
+        ('shift', scale_values.shift), ('scale', scale_values.scale),
+        ('lower_lim', scale_values.lower_lim), ('upper_lim', scale_values.upper_lim),
+        ('norm_type', norm_type), ('outlier_threshold', outlier_thresh))
+    alignment_attrs = (
+        ('mapped_start', genome_location.Start), ('mapped_strand', genome_location.Strand),
+        ('mapped_chrom', genome_location.Chrom),
+        ('clipped_bases_start', read_info.ClipStart), ('clipped_bases_end', read_info.ClipEnd),
+        ('num_insertions', read_info.Insertions), ('num_deletions', read_info.Deletions),
+        ('num_matches', read_info.Matches), ('num_mismatches', read_info.Mismatches))
+    # read_segments keeps the basecaller's segmentation so the correction can be plotted
+    alignment_datasets = (('read_alignment', np_read_align),
+                          ('genome_alignment', np_genome_align), ('read_segments', old_segs))
+    try:
+        subgroup = read_data['/Analyses/' + corrected_group].create_group(basecall_subgroup)
+        for key, value in subgroup_attrs:
+            subgroup.attrs[key] = value
+        alignment = subgroup.create_group('Alignment')
+        for key, value in alignment_attrs:
+            alignment.attrs[key] = value
+        for name, data in alignment_datasets:
+            alignment.create_dataset(name, data=data, compression='gzip')
+        events = subgroup.create_dataset('Events', data=event_data, compression='gzip')
+        events.attrs['read_start_rel_to_raw'] = read_start_rel_to_raw
+    except Exception:
+        raise NotImplementedError(msg.WRITE_BACK)
+
+    try:
+        read_data.flush()
+        read_data.close()
+    except Exception:
+        raise NotImplementedError(msg.CLOSE_AFTER_WRITE)
+    return
+
+
+def get_indel_groups(
+        alignVals, align_segs, raw_signal, min_seg_len, timeout,
+        num_cpts_limit):
+    """resquiggle.py:139-316 on the GPU (nrq_find_indels + nrq_resegment).  `raw_signal` is the
+    normalised float64 signal, as in the reference.  Change-point ties are visited in the
+    deterministic order (value desc, index desc); see DESIGN.md."""
+    from .engine import get_engine
+    read_align, genome_align = _rows(alignVals)
+    status, groups = get_engine().indel_groups(
+        read_align.encode(), genome_align.encode(), np.asarray(align_segs),
+        raw_signal, min_seg_len, timeout, num_cpts_limit)
+    exc = exception_for(status)
+    if exc is not None:
+        raise exc
+    return [indelGroupStats(s, e, cpts, [indelStats(*i) for i in indels])
+            for s, e, cpts, indels in groups]
+
+
+def _read_raw_inputs(fast5_fn, norm_type, basecall_group, subgroup):
+    """what resquiggle_read pulls out of the FAST5 file (resquiggle.py:327-347)."""
+    try:
+        fast5_data = fast5_io.open_fast5(fast5_fn, 'r')
+        channel_info = nh.get_channel_info(fast5_data)
+        raw_read = list(fast5_data['/Raw/Reads/'].values())[0]
+        all_raw_signal = fast5_io.read_dataset(raw_read['Signal'])
+        event_means, event_kmers = None, None
+        if norm_type == 'pA':
+            event_data = fast5_io.read_dataset(fast5_data[
+                '/Analyses/' + basecall_group + '/' + subgroup + '/Events'])
+            event_means = event_data['mean']
+            event_kmers = event_data['model_state']
+        fast5_data.close()
+    except Exception:
+        raise NotImplementedError(msg.OPEN_FOR_RESQUIGGLE)
+    return channel_info, all_raw_signal, event_means, event_kmers
+
+
+class _PendingRead(object):
+    __slots__ = ('fast5_fn', 'alignVals', 'genome_loc', 'starts', 'read_start', 'read_info',
+                 'raw', 'given', 'rows')
+
+    def __init__(self, fast5_fn, align_data):
+        (self.alignVals, self.genome_loc, self.starts, self.read_start,
+         self.read_info) = align_data
+        self.fast5_fn = fast5_fn
+        self.raw = None
+        self.given = None
+        self.rows = _rows(self.alignVals)
+
+
+def resquiggle_reads_batch(
+        pending, norm_type, outlier_thresh, timeout, num_cpts_limit,
+        basecall_group, corrected_group, compute_sd, pore_model,
+        min_event_obs=4, in_place=True, engine=None):
+    """The batched body of resquiggle_read (resquiggle.py:318-401) for a list of _PendingRead:
+    FAST5 read -> one device batch (a1..a7) -> FAST5 write.  Returns [(error string, read)] for
+    the reads that failed, with the reference's messages."""
+    from .batch import ReadBatch
+    from .engine import ResquiggleParams, get_engine
+    failed = []
+    ready = []
+    for pr in pending:
+        try:
+            chan, raw, ev_means, ev_kmers = _read_raw_inputs(
+                pr.fast5_fn, norm_type, basecall_group, pr.read_info.Subgroup)
+            pr.raw = np.ascontiguousarray(raw, dtype=np.int16)
+            pr.given = nh.given_shift_scale(norm_type, chan, pore_model, ev_means, ev_kmers)
+            ready.append(pr)
+        except Exception as e:  # noqa: BLE001 -- mirrors the worker's blanket except (:434)
+            failed.append((str(e), pr))
+    if not ready:
+        return failed
+    sv_in = None
+    if norm_type != 'median':
+        sv_in = np.array([[float(pr.given[0]), float(pr.given[1]), np.nan, np.nan] for pr in ready])
+    batch = ReadBatch.from_arrays(
+        [pr.raw for pr in ready], [int(pr.read_start) for pr in ready],
+        [np.asarray(pr.starts) for pr in ready],
+        [pr.rows[0].encode() for pr in ready], [pr.rows[1].encode() for pr in ready], sv_in)
+    engine = engine or get_engine()
+    params = ResquiggleParams(
+        norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=outlier_thresh,
+        compute_sd=compute_sd, num_cpts_limit=num_cpts_limit, timeout=timeout,
+        min_event_obs=min_event_obs)
+    res = engine.run(batch, params)
+    for r, pr in enumerate(ready):
+        exc = exception_for(res.status[r])
+        if exc is not None:
+            failed.append((str(exc), pr))
+            continue
+        if not in_place:
+            continue
+        try:
+            sv = res.scale_values_of(r)
+            if norm_type != 'median':
+                sv = (pr.given[0], pr.given[1], sv[2], sv[3])
+            events = res.events_of(r)
+            write_new_fast5_group(
+                pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, res.new_segs_of(r),
+                events['base'].tobytes().decode(), pr.rows, pr.starts, None,
+                nh.scaleValues(*sv), corrected_group, pr.read_info.Subgroup, norm_type,
+                outlier_thresh, compute_sd, event_data=events)
+        except Exception as e:  # noqa: BLE001
+            failed.append((str(e), pr))
+    return failed
+
+
+def resquiggle_read(
+        fast5_fn, read_start_rel_to_raw, starts_rel_to_read,
+        norm_type, outlier_thresh, alignVals,
+        timeout, num_cpts_limit, genome_loc, read_info,
+        basecall_group, corrected_group, compute_sd, pore_model,
+        min_event_obs=4, in_place=True):
+    """resquiggle.py:318-401 for one read (a device batch of one).  Raises what the reference
+    raises."""
+    pr = _PendingRead(fast5_fn, (alignVals, genome_loc, starts_rel_to_read,
+                                 read_start_rel_to_raw, read_info))
+    failed = resquiggle_reads_batch(
+        [pr], norm_type, outlier_thresh, timeout, num_cpts_limit, basecall_group,
+        corrected_group, compute_sd, pore_model, min_event_obs, in_place)
+    if failed:
+        raise _exception_from_message(failed[0][0])
+    return
+
+
+def _exception_from_message(text):
+    """rebuild the reference's exception type from its message (types per resquiggle.py)."""
+    from . import _lib
+    from .errors import STATUS_EXCEPTIONS
+    for code, cls in STATUS_EXCEPTIONS.items():
+        if _lib.status_message(code) == text:
+            return cls(text)
+    return NotImplementedError(text)
+
+
+def resquiggle_worker(
+        basecalls_q, failed_reads_q, basecall_group, corrected_group,
+        norm_type, outlier_thresh, timeout, num_cpts_limit, compute_sd,
+        pore_model):
+    """resquiggle.py:403-440 with a batching body: queue items (fast5_fn, [align_data per
+    subgroup]) are gathered until DEVICE_BATCH_READS reads are pending, then processed as one
+    device batch.  Subgroups of one file are never in the same batch, so a file is never open
+    twice (the reference's one-writer-per-file rule, :422-424)."""
+    num_processed = 0
+    done = False
+    carry = []  # later subgroups of files already seen, for following batches
+    while not done or carry:
+        pending, carry_next = [], []
+        seen_files = set()
+        for pr in carry:
+            (carry_next if pr.fast5_fn in seen_files else pending).append(pr)
+            seen_files.add(pr.fast5_fn)
+        while not done and len(pending) < DEVICE_BATCH_READS:
+            try:
+                fast5_fn, sgs_align_data = basecalls_q.get(timeout=1)
+            except queue.Empty:
+                if pending:
+                    break
+                continue
+            # None values placed in queue when all files have been processed
+            if fast5_fn is None:
+                done = True
+                break
+            num_processed += 1
+            if VERBOSE and num_processed % 100 == 0:
+                sys.stderr.write('.')
+                sys.stderr.flush()
+            for i, align_data in enumerate(sgs_align_data):
+                pr = _PendingRead(fast5_fn, align_data)
+                (pending if i == 0 else carry_next).append(pr)
+        carry = carry_next
+        if not pending:
+            continue
+        try:
+            failed = resquiggle_reads_batch(
+                pending, norm_type, outlier_thresh, timeout, num_cpts_limit,
+                basecall_group, corrected_group, compute_sd, pore_model)
+        except Exception as e:  # noqa: BLE001 -- infrastructure failure: every read of the batch fails
+            failed = [(str(e), pr) for pr in pending]
+        for text, pr in failed:
+            failed_reads_q.put((text, pr.read_info.Subgroup + ' :: ' + pr.fast5_fn))
+    return
+
+
+
+
+# orchestration and CLI entry (resquiggle.py:1037-1203) live in nanoraw_b200.pipeline
+from .pipeline import (  # noqa: E402,F401
+    ALIGN_BATCH_MULTIPLIER, args_and_main, resquiggle_all_reads, resquiggle_main)
+
+if __name__ == '__main__':
+    args_and_main()

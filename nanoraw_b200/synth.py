@@ -259,3 +259,95 @@ def config_long(seed_base=4000):
 def config_indel_dense(seed_base=5000):
     return SynthConfig(del_rate=0.12, ins_rate=0.12, clip_bases=(50, 500),
                        seed_base=seed_base)
+
+
+# ------------------------------------------------------------------------------------------
+# Front-end inputs: an Albacore-style basecall Events table and a
+# BWA-style SAM record that reproduce a SynthRead when parsed.
+BASECALL_EVENT_DTYPE = [('mean', '<f8'), ('start', '<f8'), ('stdv', '<f8'), ('length', '<f8'),
+                        ('model_state', 'S5'), ('move', '<i4')]
+
+
+def to_sam_record(read, soft_clip=(0, 0), hard_clip=(0, 0), mapq=60, seed=0):
+    """SAM fields (dict keyed like resquiggle.py:45-47) whose parse gives back read.read_align /
+    read.genome_align.  Clips are given in read orientation (start, end)."""
+    rng = np.random.default_rng(seed)
+    r = np.frombuffer(read.read_align, dtype=np.uint8)
+    g = np.frombuffer(read.genome_align, dtype=np.uint8)
+    kind = np.where(r == GAP, ord('D'), np.where(g == GAP, ord('I'), ord('M'))).astype(np.uint8)
+    cuts = np.flatnonzero(np.diff(kind)) + 1
+    bounds = np.concatenate(([0], cuts, [len(kind)]))
+    ops = [(int(b - a), chr(kind[a])) for a, b in zip(bounds[:-1], bounds[1:])]
+    seq = r[r != GAP]
+    lead = _ACGT[rng.integers(0, 4, size=soft_clip[0])]
+    tail = _ACGT[rng.integers(0, 4, size=soft_clip[1])]
+    seq = np.concatenate((lead, seq, tail)).astype(np.uint8)
+    if soft_clip[0]:
+        ops.insert(0, (soft_clip[0], 'S'))
+    if soft_clip[1]:
+        ops.append((soft_clip[1], 'S'))
+    if hard_clip[0]:
+        ops.insert(0, (hard_clip[0], 'H'))
+    if hard_clip[1]:
+        ops.append((hard_clip[1], 'H'))
+    flag = 0
+    if read.strand == '-':  # SAM stores the forward-strand view
+        ops = ops[::-1]
+        seq = _revcomp(seq)
+        flag = 16
+    cigar = ''.join('%d%s' % op for op in ops)
+    return {'qName': read.read_id or 'read', 'flag': str(flag), 'rName': read.chrom,
+            'pos': str(read.genome_start + 1), 'mapq': str(mapq), 'cigar': cigar, 'rNext': '*',
+            'pNext': '0', 'tLen': '0', 'seq': seq.tobytes().decode(), 'qual': '*'}
+
+
+def to_basecall_events(read, stay_rate=0.1, lead_stays=0, trail_stays=0, sampling_rate=4000.0,
+                       clip_bases=(0, 0), seed=0):
+    """Albacore (> 1.0) style Events for the read's basecalls: one moving event per read base,
+    plus `stay` events (move == 0) that split a base's samples, as the basecaller emits them.
+    clip_bases adds extra called bases before / after (to be soft-clipped by the mapper).
+    Returns (events, start_time_offset_samples)."""
+    rng = np.random.default_rng(seed)
+    r = np.frombuffer(read.read_align, dtype=np.uint8)
+    bases = r[r != GAP]
+    seg = np.diff(np.asarray(read.starts, dtype=np.int64))
+    if clip_bases[0] or clip_bases[1]:
+        pre = _ACGT[rng.integers(0, 4, size=clip_bases[0])]
+        post = _ACGT[rng.integers(0, 4, size=clip_bases[1])]
+        bases = np.concatenate((pre, bases, post)).astype(np.uint8)
+        seg = np.concatenate((rng.integers(3, 15, size=clip_bases[0]), seg,
+                              rng.integers(3, 15, size=clip_bases[1])))
+    lengths, moves, states = [], [], []
+    padded = np.concatenate(([bases[0]] * 2, bases, [bases[-1]] * 2)).astype(np.uint8)
+
+    def kmer(i):
+        return padded[i:i + 5].tobytes()
+
+    for _ in range(lead_stays):
+        lengths.append(int(rng.integers(2, 9)))
+        moves.append(0)
+        states.append(kmer(0))
+    for i, n in enumerate(seg.tolist()):
+        parts = [n]
+        if n >= 4 and rng.random() < stay_rate:
+            cut = int(rng.integers(1, n))
+            parts = [cut, n - cut]
+        for j, p in enumerate(parts):
+            lengths.append(p)
+            moves.append(1 if j == 0 else 0)
+            states.append(kmer(i))
+    for _ in range(trail_stays):
+        lengths.append(int(rng.integers(2, 9)))
+        moves.append(0)
+        states.append(kmer(len(bases) - 1))
+    lengths = np.asarray(lengths, dtype=np.int64)
+    ev = np.zeros(len(lengths), dtype=BASECALL_EVENT_DTYPE)
+    begin = np.concatenate(([0], np.cumsum(lengths)[:-1]))
+    ev['start'] = begin / sampling_rate
+    ev['length'] = lengths / sampling_rate
+    ev['mean'] = 90.0 + rng.standard_normal(len(lengths)) * 10.0
+    ev['stdv'] = 1.5
+    ev['model_state'] = states
+    ev['move'] = moves
+    ev['move'][0] = 1
+    return ev

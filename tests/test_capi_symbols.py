@@ -50,7 +50,7 @@ def test_params_struct_layout():
     assert C.sizeof(_lib.NrqParams) == 48
     assert _lib.NrqParams.outlier_thresh.offset == 8
     assert _lib.NrqParams.timeout_ns.offset == 32
-    assert C.sizeof(_lib.NrqBatch) == 80
+    assert C.sizeof(_lib.NrqBatch) == 96
     assert C.sizeof(_lib.NrqResults) == 88
 
 
