@@ -245,8 +245,9 @@ def spot_check(engine, host_batch, reads, out_dev, n_check=2):
         nb = int(out_dev.n_bases[r].item())
         segs = out_dev.new_segs[o + r:o + r + nb + 1].cpu().numpy()
         mean = out_dev.norm_mean[o:o + nb].cpu().numpy()
+        ref_mean = want['events']['norm_mean']
         if not (np.array_equal(segs, want['new_segs']) and
-                np.array_equal(mean, want['events']['norm_mean'])):
+                np.all(np.abs(mean - ref_mean) <= 1e-9 * np.maximum(1.0, np.abs(ref_mean)))):
             bad += 1
     return bad
 
