@@ -275,10 +275,42 @@ __device__ __forceinline__ long long global_ns() {
   return t;
 }
 
+// splice (:362-372) + validation (:373-387), cooperative over one warp: finished change-points already sit in
+// their new_segs slots; copy the untouched boundaries between groups and check the result
+__device__ int splice_and_validate(const SegCtx& c, int n_bases, int n_norm, int& region_samples) {
+  const unsigned lane = lane_id();
+  int dtotal = 0;
+  if (c.n_ind > 0) {
+    int4 z = c.ind[c.n_ind - 1];
+    dtotal = z.w + z.z;
+  }
+  int prev_stop = 0;
+  for (int g = 0; g <= c.ng; ++g) {
+    if (g < c.ng) {
+      int4 grp = c.groups[g];
+      int d = c.ind[grp.z].w;
+      for (int j = prev_stop + (int)lane; j <= grp.x; j += 32) c.out[j + d] = c.t[j];
+      prev_stop = grp.y;
+      region_samples += c.t[grp.y] - c.t[grp.x];
+    } else {
+      for (int j = prev_stop + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = c.t[j];
+    }
+  }
+  __syncwarp();
+  const int total = c.last + 1 + dtotal;
+  int zero_len = 0;
+  for (int i = lane; i + 1 < total; i += 32) zero_len |= (c.out[i + 1] - c.out[i] < 1);
+  zero_len = __any_sync(kFull, zero_len);
+  if (zero_len) return NRQ_ST_ZERO_LEN;
+  if (c.out[0] < 0) return NRQ_ST_NEG_START;
+  if (c.out[total - 1] > n_norm) return NRQ_ST_PAST_END;
+  if (total != n_bases + 1) return NRQ_ST_SEQ_MISMATCH;
+  return NRQ_ST_OK;
+}
+
 __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm, int& region_samples) {
   const unsigned lane = lane_id();
   const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
-  int dtotal = 0;
   if (c.n_ind > 0) {
     int lo = 0, hi = 0, maxend = c.ind[0].y;
     int start, stop;
@@ -310,35 +342,8 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     if (lane == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
     __syncwarp();
     ++c.ng;
-    int4 z = c.ind[c.n_ind - 1];
-    dtotal = z.w + z.z;
   }
-  // splice (:362-372): untouched boundaries between groups
-  int prev_stop = 0;
-  for (int g = 0; g <= c.ng; ++g) {
-    int upto, d;
-    if (g < c.ng) {
-      int4 grp = c.groups[g];
-      upto = grp.x;
-      d = c.ind[grp.z].w;
-      for (int j = prev_stop + (int)lane; j <= upto; j += 32) c.out[j + d] = c.t[j];
-      prev_stop = grp.y;
-      region_samples += c.t[grp.y] - c.t[grp.x];
-    } else {
-      for (int j = prev_stop + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = c.t[j];
-    }
-  }
-  __syncwarp();
-  // validation (:373-387)
-  const int total = c.last + 1 + dtotal;
-  int zero_len = 0;
-  for (int i = lane; i + 1 < total; i += 32) zero_len |= (c.out[i + 1] - c.out[i] < 1);
-  zero_len = __any_sync(kFull, zero_len);
-  if (zero_len) return NRQ_ST_ZERO_LEN;
-  if (c.out[0] < 0) return NRQ_ST_NEG_START;
-  if (c.out[total - 1] > n_norm) return NRQ_ST_PAST_END;
-  if (total != n_bases + 1) return NRQ_ST_SEQ_MISMATCH;
-  return NRQ_ST_OK;
+  return splice_and_validate(c, n_bases, n_norm, region_samples);
 }
 
 #ifndef NRQ_SEG_MINB

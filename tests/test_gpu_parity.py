@@ -232,3 +232,4 @@ def test_host_buffer_entry_point(engine):
         assert np.array_equal(outs['new_segs'][o + r:o + r + n + 1], want.new_segs_of(r))
         assert np.array_equal(outs['norm_mean'][o:o + n], want.norm_mean[o:o + n])
         assert np.array_equal(outs['norm_stdev'][o:o + n], want.norm_stdev[o:o + n])
+
