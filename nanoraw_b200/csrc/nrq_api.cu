@@ -2,6 +2,7 @@
 // below; this file only validates arguments, carves the workspace and launches.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -288,15 +289,28 @@ int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const 
 }
 
 // ------------------------------------------------------------------ host-buffer entry point
-struct nrq_handle {
-  int device;
-  cudaStream_t stream;
-  std::vector<std::pair<void*, size_t>> pool;  // grow-only device buffers, by slot
+// The batch is cut into chunks of reads that flow through kSlots independent (stream, device buffers) sets:
+// chunk c+1's host->device copies overlap chunk c's kernels and chunk c-1's device->host copies, and the two
+// PCIe directions run concurrently.  Per-chunk CSR offsets are rebased on the host into pinned staging.
+constexpr int kSlots = 3;
+constexpr int64_t kChunkBytesDefault = 96ll << 20;  // target input bytes per chunk (NRQ_HOST_CHUNK_BYTES overrides)
+
+struct nrq_slot {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
+  std::vector<std::pair<void*, size_t>> dev;  // grow-only device buffers
+  int64_t* off_stage = nullptr;               // pinned: 3 rebased offset arrays
+  size_t off_stage_elems = 0;
 };
 
-static void* slot(nrq_handle* h, size_t idx, size_t bytes, cudaError_t* err) {
-  if (h->pool.size() <= idx) h->pool.resize(idx + 1, {nullptr, 0});
-  auto& s = h->pool[idx];
+struct nrq_handle {
+  int device;
+  nrq_slot slots[kSlots];
+};
+
+static void* dev_buf(nrq_slot& sl, size_t idx, size_t bytes, cudaError_t* err) {
+  if (sl.dev.size() <= idx) sl.dev.resize(idx + 1, {nullptr, 0});
+  auto& s = sl.dev[idx];
   if (s.second < bytes) {
     if (s.first) cudaFree(s.first);
     size_t want = bytes + bytes / 4 + 256;
@@ -311,10 +325,13 @@ nrq_handle* nrq_create(int32_t device) {
   if (cudaSetDevice(device) != cudaSuccess) { fail("nrq_create: cudaSetDevice failed"); return nullptr; }
   nrq_handle* h = new nrq_handle();
   h->device = device;
-  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
-    delete h;
-    fail("nrq_create: stream creation failed");
-    return nullptr;
+  for (auto& sl : h->slots) {
+    if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) {
+      nrq_destroy(h);
+      fail("nrq_create: stream / event creation failed");
+      return nullptr;
+    }
   }
   return h;
 }
@@ -322,8 +339,12 @@ nrq_handle* nrq_create(int32_t device) {
 void nrq_destroy(nrq_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  for (auto& s : h->pool) if (s.first) cudaFree(s.first);
-  cudaStreamDestroy(h->stream);
+  for (auto& sl : h->slots) {
+    for (auto& s : sl.dev) if (s.first) cudaFree(s.first);
+    if (sl.off_stage) cudaFreeHost(sl.off_stage);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.stream) cudaStreamDestroy(sl.stream);
+  }
   delete h;
 }
 
@@ -336,67 +357,117 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
   if (R == 0) return 0;
   cudaError_t ce = cudaSetDevice(h->device);
   if (ce != cudaSuccess) return fail("cudaSetDevice", ce);
-  const int64_t n_raw = b->raw_off[R], n_starts = b->starts_off[R], n_align = b->align_off[R];
-  cudaStream_t s = h->stream;
   cudaError_t err = cudaSuccess;
-  size_t k = 0;
-  auto up = [&](const void* src, size_t bytes) -> void* {
-    void* d = slot(h, k++, bytes ? bytes : 1, &err);
-    if (d && bytes && src) {
-      cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s);
-      if (e != cudaSuccess) err = e;
+  int rc = 0;
+
+  int64_t kChunkBytes = kChunkBytesDefault;
+  if (const char* env = getenv("NRQ_HOST_CHUNK_BYTES")) {
+    long long v = atoll(env);
+    if (v > 0) kChunkBytes = v;
+  }
+  int chunk_index = 0;
+  for (int lo = 0; lo < R && rc == 0 && err == cudaSuccess; ++chunk_index) {
+    // ---- next chunk: reads [lo, hi) holding about kChunkBytes of input
+    int hi = lo;
+    auto in_bytes = [&](int a, int z) {
+      return 2 * (b->raw_off[z] - b->raw_off[a]) + 4 * (b->starts_off[z] - b->starts_off[a]) +
+             2 * (b->align_off[z] - b->align_off[a]);
+    };
+    while (hi < R && (hi == lo || in_bytes(lo, hi + 1) <= kChunkBytes)) ++hi;
+    const int n = hi - lo;
+    nrq_slot& sl = h->slots[chunk_index % kSlots];
+    cudaStream_t s = sl.stream;
+    // the slot's pinned offset staging is rewritten below: wait for its previous chunk to finish
+    ce = cudaEventSynchronize(sl.done);
+    if (ce != cudaSuccess) { err = ce; break; }
+    const size_t need = 3 * (size_t)(n + 1);
+    if (sl.off_stage_elems < need) {
+      if (sl.off_stage) cudaFreeHost(sl.off_stage);
+      sl.off_stage = nullptr;
+      sl.off_stage_elems = 0;
+      ce = cudaMallocHost(&sl.off_stage, 8 * (need + need / 4));
+      if (ce != cudaSuccess) { err = ce; break; }
+      sl.off_stage_elems = need + need / 4;
     }
-    return d;
-  };
-  nrq_batch d = *b;
-  d.norm_signal = nullptr;  // the host entry point always normalises from raw
-  d.norm_off = nullptr;
-  d.raw = (const int16_t*)up(b->raw, 2 * (size_t)n_raw);
-  d.raw_off = (const int64_t*)up(b->raw_off, 8 * (size_t)(R + 1));
-  d.read_start = (const int32_t*)up(b->read_start, 4 * (size_t)R);
-  d.starts = (const int32_t*)up(b->starts, 4 * (size_t)n_starts);
-  d.starts_off = (const int64_t*)up(b->starts_off, 8 * (size_t)(R + 1));
-  d.read_align = (const uint8_t*)up(b->read_align, (size_t)n_align);
-  d.genome_align = (const uint8_t*)up(b->genome_align, (size_t)n_align);
-  d.align_off = (const int64_t*)up(b->align_off, 8 * (size_t)(R + 1));
-  d.scale_values_in = b->scale_values_in ? (const double*)up(b->scale_values_in, 32 * (size_t)R) : nullptr;
-  if (!b->scale_values_in) ++k;
-  nrq_results o;
-  o.status = (int32_t*)up(nullptr, 4 * (size_t)R);
-  o.n_bases = (int32_t*)up(nullptr, 4 * (size_t)R);
-  o.n_indels = (int32_t*)up(nullptr, 4 * (size_t)R);
-  o.scale_values = (double*)up(nullptr, 32 * (size_t)R);
-  o.new_segs = (int32_t*)up(nullptr, 4 * (size_t)(n_align + R));
-  o.norm_mean = (double*)up(nullptr, 8 * (size_t)n_align);
-  o.norm_stdev = (double*)up(nullptr, 8 * (size_t)n_align);
-  o.ev_start = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
-  o.ev_length = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
-  o.ev_base = (uint8_t*)up(nullptr, (size_t)n_align);
-  o.region_samples = (int32_t*)up(nullptr, 4 * (size_t)R);
-  int64_t ws_bytes = nrq_workspace_bytes(R, n_align, p);
-  void* ws = up(nullptr, (size_t)ws_bytes);
-  if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host: staging", err);
-  if (int e = nrq_resquiggle_batch(&d, p, &o, ws, ws_bytes, s)) return e;
-  auto down = [&](void* dst, const void* src, size_t bytes) {
-    if (dst && bytes) {
-      cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
-      if (e != cudaSuccess) err = e;
+    int64_t* raw_off = sl.off_stage;
+    int64_t* starts_off = raw_off + (n + 1);
+    int64_t* align_off = starts_off + (n + 1);
+    const int64_t raw0 = b->raw_off[lo], st0 = b->starts_off[lo], al0 = b->align_off[lo];
+    for (int i = 0; i <= n; ++i) {
+      raw_off[i] = b->raw_off[lo + i] - raw0;
+      starts_off[i] = b->starts_off[lo + i] - st0;
+      align_off[i] = b->align_off[lo + i] - al0;
     }
-  };
-  down(out->status, o.status, 4 * (size_t)R);
-  down(out->n_bases, o.n_bases, 4 * (size_t)R);
-  down(out->n_indels, o.n_indels, 4 * (size_t)R);
-  down(out->scale_values, o.scale_values, 32 * (size_t)R);
-  down(out->new_segs, o.new_segs, 4 * (size_t)(n_align + R));
-  down(out->norm_mean, o.norm_mean, 8 * (size_t)n_align);
-  down(out->norm_stdev, o.norm_stdev, 8 * (size_t)n_align);
-  down(out->ev_start, o.ev_start, 4 * (size_t)n_align);
-  down(out->ev_length, o.ev_length, 4 * (size_t)n_align);
-  down(out->ev_base, o.ev_base, (size_t)n_align);
-  down(out->region_samples, o.region_samples, 4 * (size_t)R);
-  if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host: readback", err);
-  ce = cudaStreamSynchronize(s);
-  if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_host: sync", ce);
+    const int64_t n_raw = raw_off[n], n_starts = starts_off[n], n_align = align_off[n];
+
+    size_t k = 0;
+    auto up = [&](const void* src, size_t bytes) -> void* {
+      void* d = dev_buf(sl, k++, bytes ? bytes : 1, &err);
+      if (d && bytes && src) {
+        cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) err = e;
+      }
+      return d;
+    };
+    nrq_batch d = *b;
+    d.n_reads = n;
+    d.norm_signal = nullptr;  // the host entry point always normalises from raw
+    d.norm_off = nullptr;
+    d.raw = (const int16_t*)up(b->raw + raw0, 2 * (size_t)n_raw);
+    d.raw_off = (const int64_t*)up(raw_off, 8 * (size_t)(n + 1));
+    d.read_start = (const int32_t*)up(b->read_start + lo, 4 * (size_t)n);
+    d.starts = (const int32_t*)up(b->starts + st0, 4 * (size_t)n_starts);
+    d.starts_off = (const int64_t*)up(starts_off, 8 * (size_t)(n + 1));
+    d.read_align = (const uint8_t*)up(b->read_align + al0, (size_t)n_align);
+    d.genome_align = (const uint8_t*)up(b->genome_align + al0, (size_t)n_align);
+    d.align_off = (const int64_t*)up(align_off, 8 * (size_t)(n + 1));
+    d.scale_values_in = b->scale_values_in ? (const double*)up(b->scale_values_in + 4 * (size_t)lo, 32 * (size_t)n)
+                                           : nullptr;
+    if (!b->scale_values_in) ++k;
+    nrq_results o;
+    o.status = (int32_t*)up(nullptr, 4 * (size_t)n);
+    o.n_bases = (int32_t*)up(nullptr, 4 * (size_t)n);
+    o.n_indels = (int32_t*)up(nullptr, 4 * (size_t)n);
+    o.scale_values = (double*)up(nullptr, 32 * (size_t)n);
+    o.new_segs = (int32_t*)up(nullptr, 4 * (size_t)(n_align + n));
+    o.norm_mean = (double*)up(nullptr, 8 * (size_t)n_align);
+    o.norm_stdev = (double*)up(nullptr, 8 * (size_t)n_align);
+    o.ev_start = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
+    o.ev_length = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
+    o.ev_base = (uint8_t*)up(nullptr, (size_t)n_align);
+    o.region_samples = (int32_t*)up(nullptr, 4 * (size_t)n);
+    int64_t ws_bytes = nrq_workspace_bytes(n, n_align, p);
+    void* ws = up(nullptr, (size_t)ws_bytes);
+    if (err != cudaSuccess) break;
+    rc = nrq_resquiggle_batch(&d, p, &o, ws, ws_bytes, s);
+    if (rc) break;
+    auto down = [&](void* dst, const void* src, size_t bytes) {
+      if (dst && bytes) {
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+        if (e != cudaSuccess) err = e;
+      }
+    };
+    auto at = [](auto* base, int64_t elems) { return base ? base + elems : base; };
+    down(at(out->status, lo), o.status, 4 * (size_t)n);
+    down(at(out->n_bases, lo), o.n_bases, 4 * (size_t)n);
+    down(at(out->n_indels, lo), o.n_indels, 4 * (size_t)n);
+    down(at(out->scale_values, 4 * (int64_t)lo), o.scale_values, 32 * (size_t)n);
+    down(at(out->new_segs, al0 + lo), o.new_segs, 4 * (size_t)(n_align + n));
+    down(at(out->norm_mean, al0), o.norm_mean, 8 * (size_t)n_align);
+    down(at(out->norm_stdev, al0), o.norm_stdev, 8 * (size_t)n_align);
+    down(at(out->ev_start, al0), o.ev_start, 4 * (size_t)n_align);
+    down(at(out->ev_length, al0), o.ev_length, 4 * (size_t)n_align);
+    down(at(out->ev_base, al0), o.ev_base, (size_t)n_align);
+    down(at(out->region_samples, lo), o.region_samples, 4 * (size_t)n);
+    cudaEventRecord(sl.done, s);
+    lo = hi;
+  }
+  for (auto& sl : h->slots) {
+    cudaError_t e = cudaStreamSynchronize(sl.stream);
+    if (e != cudaSuccess && err == cudaSuccess) err = e;
+  }
+  if (rc) return rc;
+  if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host", err);
   return 0;
 }
 

@@ -195,12 +195,16 @@ def test_unsatisfiable_region_terminates(engine):
             assert res.ok(r) and np.array_equal(res.new_segs_of(r), out['new_segs'])
 
 
-def test_host_buffer_entry_point(engine):
-    """nrq_resquiggle_batch_host (host pointers in/out) == the torch-managed route."""
+@pytest.mark.parametrize('chunk_bytes', [None, 150_000])
+def test_host_buffer_entry_point(engine, chunk_bytes, monkeypatch):
+    """nrq_resquiggle_batch_host (host pointers in/out) == the torch-managed route; with a small
+    chunk size the batch flows through the multi-stream pipeline in many chunks."""
     import ctypes as C
     from nanoraw_b200 import _lib
     from nanoraw_b200.engine import ResquiggleParams
-    reads = synth.make_reads(5, synth.config_short(47000), genome=synth.make_genome(200_000, seed=9))
+    if chunk_bytes:
+        monkeypatch.setenv('NRQ_HOST_CHUNK_BYTES', str(chunk_bytes))
+    reads = synth.make_reads(11, synth.config_short(47000), genome=synth.make_genome(200_000, seed=9))
     batch = ReadBatch.from_reads(reads)
     params = ResquiggleParams()
     want = engine.run(batch, params)
@@ -227,9 +231,13 @@ def test_host_buffer_entry_point(engine):
     _lib.check(lib.nrq_resquiggle_batch_host(h, C.byref(hb), C.byref(pc), C.byref(hr)), 'host batch')
     lib.nrq_destroy(h)
     assert np.array_equal(outs['status'], want.status)
+    assert np.array_equal(outs['n_bases'], want.n_bases)
+    assert np.array_equal(outs['scale_values'].reshape(-1, 4), want.scale_values)
     for r in range(R):
         o, n = int(batch.align_off[r]), int(want.n_bases[r])
         assert np.array_equal(outs['new_segs'][o + r:o + r + n + 1], want.new_segs_of(r))
         assert np.array_equal(outs['norm_mean'][o:o + n], want.norm_mean[o:o + n])
         assert np.array_equal(outs['norm_stdev'][o:o + n], want.norm_stdev[o:o + n])
+        assert np.array_equal(outs['ev_base'][o:o + n], want.ev_base[o:o + n])
+        assert np.array_equal(outs['ev_start'][o:o + n], want.ev_start[o:o + n])
 
