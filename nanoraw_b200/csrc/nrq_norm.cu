@@ -1,7 +1,9 @@
 // K1 -- the order statistics of normalize_raw_signal (nanoraw/nanoraw_helper.py:240-256).
 //
-// One CTA per read.  Fast path: a single streaming pass builds a shared-memory histogram of the
-// int16 DAC values over a window of kWin values centred on a pivot sample; both medians of the
+// One CTA per read, eight CTAs per SM (the kernel is a latency-bound stream of shared-memory atomics: occupancy
+// is what buys bandwidth, so the histogram window is kept to 8 KB).  Fast path: a single streaming pass builds a
+// shared-memory histogram of the int16 DAC values over a window of kWin values centred on a pivot (median of
+// three samples); both medians of the
 // 'median' normalisation are then exact integer selects on that histogram (SURVEY.md section 8a
 // exactness notes: shift is in Z/2, |raw-shift| in Z/2, median(x) == +0.0, mad from the same two
 // middle order statistics).  Reads whose needed ranks fall outside the window take the general
@@ -13,7 +15,13 @@
 namespace nrq {
 
 constexpr int kNormThreads = 256;
-constexpr int kWin = 8192;  // histogram window, in DAC values (32 KB of shared memory)
+#ifndef NRQ_NORM_WIN
+#define NRQ_NORM_WIN 2048
+#endif
+#ifndef NRQ_NORM_MINB
+#define NRQ_NORM_MINB 8
+#endif
+constexpr int kWin = NRQ_NORM_WIN;  // histogram window, in DAC values (4 bytes of shared memory each)
 
 // ---------------------------------------------------------------- block primitives
 __device__ __forceinline__ long long block_sum(long long v, long long* sh) {
@@ -57,13 +65,20 @@ __device__ __forceinline__ void for_each_sample(const int16_t* __restrict__ sig,
   for (int i = tid; i < head; i += kNormThreads) f((int)sig[i]);
   const int4* v = reinterpret_cast<const int4*>(sig + head);
   int nv = (n - head) >> 3;
-  for (int i = tid; i < nv; i += kNormThreads) {
-    int4 q = __ldg(v + i);
+  auto eight = [&](const int4& q) {
     f((int)(short)(q.x & 0xffff)); f((int)(short)(q.x >> 16));
     f((int)(short)(q.y & 0xffff)); f((int)(short)(q.y >> 16));
     f((int)(short)(q.z & 0xffff)); f((int)(short)(q.z >> 16));
     f((int)(short)(q.w & 0xffff)); f((int)(short)(q.w >> 16));
+  };
+  int i = tid;
+  // four 128-bit loads in flight per thread before any of them is consumed
+  for (; i + 3 * kNormThreads < nv; i += 4 * kNormThreads) {
+    int4 q0 = __ldg(v + i), q1 = __ldg(v + i + kNormThreads);
+    int4 q2 = __ldg(v + i + 2 * kNormThreads), q3 = __ldg(v + i + 3 * kNormThreads);
+    eight(q0); eight(q1); eight(q2); eight(q3);
   }
+  for (; i < nv; i += kNormThreads) eight(__ldg(v + i));
   for (int i = head + (nv << 3) + tid; i < n; i += kNormThreads) f((int)sig[i]);
 }
 
@@ -121,7 +136,7 @@ __device__ __forceinline__ unsigned long long dbits(double x) {
 }
 
 // ---------------------------------------------------------------- K1
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, NRQ_NORM_MINB)
 k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __restrict__ sv_out) {
   __shared__ unsigned hist[kWin];
   __shared__ long long sh_red[kNormThreads / 32];
@@ -159,7 +174,11 @@ k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __
   bool win_ok = false;
   if (need_hist && !force_general) {
     for (int i = tid; i < kWin; i += kNormThreads) hist[i] = 0;
-    lo_w = (int)sig[n / 2] - kWin / 2;
+    {  // pivot: median of three samples, so that a single spike cannot misplace the window
+      int a = sig[n / 4], c = sig[n / 2], e = sig[(3 * (long long)n) / 4];
+      int piv = max(min(a, c), min(max(a, c), e));
+      lo_w = piv - kWin / 2;
+    }
     __syncthreads();
     int nb = 0, na = 0;
     for_each_sample(sig, n, [&](int v) {
