@@ -17,8 +17,14 @@
 namespace nrq {
 
 constexpr int kSegWarps = 8;
-constexpr int kRegionCap = 254;  // region samples held in shared memory per warp (p99 of real regions ~200)
-constexpr int kSegLut = 512;     // DAC codes covered by the per-warp table of normalised values
+#ifndef NRQ_SEG_CAP
+#define NRQ_SEG_CAP 254
+#endif
+#ifndef NRQ_SEG_LUT
+#define NRQ_SEG_LUT 256
+#endif
+constexpr int kRegionCap = NRQ_SEG_CAP;  // region samples held in shared memory per warp (p99 of real regions ~200)
+constexpr int kSegLut = NRQ_SEG_LUT;     // DAC codes covered by the per-warp table of normalised values
 constexpr unsigned kFull = 0xffffffffu;
 
 struct SegCtx {
@@ -347,7 +353,7 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
 }
 
 #ifndef NRQ_SEG_MINB
-#define NRQ_SEG_MINB 4
+#define NRQ_SEG_MINB 6
 #endif
 __global__ void __launch_bounds__(kSegWarps * 32, NRQ_SEG_MINB)
 k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int64_t* __restrict__ indel_off,
@@ -387,8 +393,10 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     if (c.coef.clip) {
       double e0 = c.coef.shift + c.coef.lo * c.coef.scale, e1 = c.coef.shift + c.coef.hi * c.coef.scale;
       double lo = fmin(e0, e1), hi = fmax(e0, e1);
-      if (isfinite(lo) && isfinite(hi) && hi - lo < (double)(kSegLut - 4) && lo > -40000.0 && hi < 40000.0)
-        c.lut_lo = (int)floor(lo) - 2;
+      if (isfinite(lo) && isfinite(hi) && lo > -40000.0 && hi < 40000.0) {
+        if (hi - lo < (double)(kSegLut - 4)) c.lut_lo = (int)floor(lo) - 2;         // every unclipped code
+        else c.lut_lo = (int)floor(0.5 * (lo + hi)) - kSegLut / 2;                  // the middle of them
+      }
     }
     __syncwarp();
     for (int k = lane; k < kSegLut; k += 32) lut[warp][k] = norm_value(c.lut_lo + k, c.coef);
