@@ -1,0 +1,125 @@
+"""Size-independent properties of the CUDA path on batches far larger than the oracle can check
+read by read (SURVEY.md section 4 invariants + invariances the arithmetic guarantees)."""
+import numpy as np
+import pytest
+
+from nanoraw_b200 import synth
+from nanoraw_b200.batch import ReadBatch
+
+pytestmark = pytest.mark.gpu
+
+N_READS = 600
+
+
+@pytest.fixture(scope='module')
+def engine():
+    from nanoraw_b200.engine import ResquiggleEngine
+    return ResquiggleEngine()
+
+
+@pytest.fixture(scope='module')
+def reads():
+    cfgs = [synth.SynthConfig(span_mean=3000, span_sd=800, seed_base=61000),
+            synth.SynthConfig(span_mean=2500, span_sd=500, del_rate=0.12, ins_rate=0.12,
+                              clip_bases=(20, 200), seed_base=62000),
+            synth.SynthConfig(span_mean=2000, span_sd=400, dwell_mean=6.4, seed_base=63000)]
+    genome = synth.make_genome(1_000_000, seed=17)
+    out = []
+    for i in range(N_READS):
+        cfg = cfgs[i % len(cfgs)]
+        out.append(synth.make_read(genome, synth.kmer_levels(cfg), cfg, i))
+    return out
+
+
+@pytest.fixture(scope='module')
+def result(engine, reads):
+    from nanoraw_b200.engine import ResquiggleParams
+    return engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+
+
+def test_every_read_succeeds_and_segments_are_valid(reads, result):
+    assert (result.status == 0).all()
+    for r, read in enumerate(reads):
+        segs = result.new_segs_of(r)
+        g = np.frombuffer(read.genome_align, dtype=np.uint8)
+        n_genome = int((g != ord('-')).sum())
+        assert len(segs) == n_genome + 1 == int(result.n_bases[r]) + 1     # resquiggle.py:384-387
+        assert segs[0] == 0 and segs[-1] == read.n_samples                  # :376-381
+        assert np.diff(segs).min() >= 1                                     # :373-375
+        ev = result.events_of(r)
+        assert np.array_equal(ev['start'], segs[:-1]) and np.array_equal(ev['length'], np.diff(segs))
+        assert ev['base'].tobytes() == g[g != ord('-')].tobytes()
+        assert int(ev['length'].sum()) == read.n_samples
+        # boundaries that are not basecaller boundaries were placed by the change-point search, which
+        # keeps min_seg_len = 4 samples between neighbours (resquiggle.py:241-255)
+        new = ~np.isin(segs, read.starts)
+        idx = np.flatnonzero(new)
+        assert (segs[idx] - segs[idx - 1] >= 4).all() and (segs[idx + 1] - segs[idx] >= 4).all()
+
+
+def test_event_means_reassemble_the_signal_mean(engine, reads, result):
+    """sum(mean_k * length_k) over a read == sum of its normalised signal"""
+    from nanoraw_b200.engine import ResquiggleParams
+    sub = list(range(0, N_READS, 25))
+    db = engine.upload(ReadBatch.from_reads([reads[r] for r in sub]))
+    _, sv, sigs = engine.normalize_signal(db, ResquiggleParams())
+    for k, r in enumerate(sub):
+        ev = result.events_of(r)
+        total = float((ev['norm_mean'] * ev['length']).sum())
+        assert abs(total - float(sigs[k].sum())) <= 1e-9 * max(1.0, np.abs(sigs[k]).sum())
+        assert tuple(sv[k]) == tuple(result.scale_values[r])
+        assert sigs[k].min() >= sv[k][2] and sigs[k].max() <= sv[k][3]     # winsorised to the limits
+
+
+def test_integer_statistics_agree_with_numpy_order_kernel(engine, reads, result):
+    from nanoraw_b200.engine import ResquiggleParams
+    exact = engine.run(ReadBatch.from_reads(reads), ResquiggleParams(exact_stats=True))
+    for r in range(N_READS):
+        assert np.array_equal(exact.new_segs_of(r), result.new_segs_of(r))
+        a, b = exact.events_of(r), result.events_of(r)
+        assert np.max(np.abs(a['norm_mean'] - b['norm_mean'])) < 1e-12
+        assert np.max(np.abs(a['norm_stdev'] - b['norm_stdev'])) < 1e-11
+
+
+def test_results_do_not_depend_on_batch_composition(engine, reads, result):
+    """reads are independent: reversing the batch order, or running a slice, changes nothing per read"""
+    from nanoraw_b200.engine import ResquiggleParams
+    rev = engine.run(ReadBatch.from_reads(reads[::-1]), ResquiggleParams())
+    for r in range(0, N_READS, 7):
+        q = N_READS - 1 - r
+        assert np.array_equal(rev.new_segs_of(q), result.new_segs_of(r))
+        assert np.array_equal(rev.events_of(q)['norm_mean'], result.events_of(r)['norm_mean'])
+        assert np.array_equal(rev.scale_values[q], result.scale_values[r], equal_nan=True)
+    again = engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+    assert np.array_equal(again.status, result.status)
+    for r in range(N_READS):  # bit-identical from run to run (no atomics on the data path)
+        assert np.array_equal(again.new_segs_of(r), result.new_segs_of(r))
+        assert np.array_equal(again.events_of(r), result.events_of(r))
+
+
+def test_translation_and_power_of_two_scaling_invariance(engine, reads, result):
+    """raw + c shifts `shift` by c and raw * 2 doubles shift and scale; the normalised signal is then
+    bit-identical (all exact in float64), so boundaries and event statistics must not move"""
+    from nanoraw_b200.engine import ResquiggleParams
+    import copy
+    sub = reads[:120]
+    moved, doubled = [], []
+    for rd in sub:
+        a = copy.copy(rd)
+        a.raw = (rd.raw.astype(np.int32) + 321).astype(np.int16)
+        moved.append(a)
+        b = copy.copy(rd)
+        b.raw = (rd.raw.astype(np.int32) * 2).astype(np.int16)
+        doubled.append(b)
+    rm = engine.run(ReadBatch.from_reads(moved), ResquiggleParams())
+    rd2 = engine.run(ReadBatch.from_reads(doubled), ResquiggleParams())
+    for r in range(len(sub)):
+        assert np.array_equal(rm.new_segs_of(r), result.new_segs_of(r))
+        assert np.array_equal(rd2.new_segs_of(r), result.new_segs_of(r))
+        sv, svm, svd = result.scale_values[r], rm.scale_values[r], rd2.scale_values[r]
+        assert svm[0] == sv[0] + 321 and svm[1] == sv[1] and svd[0] == 2 * sv[0] and svd[1] == 2 * sv[1]
+        assert np.array_equal(svm[2:], sv[2:]) and np.array_equal(svd[2:], sv[2:])
+        ev = result.events_of(r)
+        for other in (rm.events_of(r), rd2.events_of(r)):
+            assert np.max(np.abs(other['norm_mean'] - ev['norm_mean'])) < 1e-12
+            assert np.max(np.abs(other['norm_stdev'] - ev['norm_stdev'])) < 1e-11
