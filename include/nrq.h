@@ -156,6 +156,12 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
                   int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
                   int32_t* n_groups, void* stream);
 
+/* f-4: the running-difference trace of plot_correction (plot_commands.py:225-229) over one window of an already
+ * normalised signal (device pointers): out[i] = |2 cs[i+m] - cs[i] - cs[i+2m]|, i in [0, n - 2m], cs the
+ * sequential float64 cumulative sum.  scratch: n + 1 doubles. */
+int nrq_running_diffs(const double* signal, int32_t n, int32_t min_seg_len, double* scratch, double* out,
+                      void* stream);
+
 /* a7: per-base mean / sd / start / length / base (resquiggle.py:60-70). */
 int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                     const int32_t* n_bases, const int32_t* new_segs, const int32_t* status,

@@ -49,6 +49,7 @@ SYMBOLS = {
     'nrq_normalize_signal': (C.c_int, [C.POINTER(NrqBatch), _P, _P, _P, _P, _P]),
     'nrq_resegment': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
                                 C.c_int64, _P, _P, _P, _P, _P, _P]),
+    'nrq_running_diffs': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     'nrq_event_table': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P]),
     'nrq_resquiggle_batch': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams),

@@ -208,6 +208,16 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
   return 0;
 }
 
+int nrq_running_diffs(const double* signal, int32_t n, int32_t min_seg_len, double* scratch, double* out,
+                      void* stream) {
+  if (!signal || !scratch || !out) return fail("nrq_running_diffs: NULL argument");
+  if (n < 0 || min_seg_len < 1) return fail("nrq_running_diffs: bad size");
+  if (n - 2 * min_seg_len + 1 <= 0) return 0;
+  nrq::k_running_diffs<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(signal, n, min_seg_len, scratch, out);
+  NRQ_CHECK_LAUNCH("k_running_diffs");
+  return 0;
+}
+
 int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                     const int32_t* n_bases, const int32_t* new_segs, const int32_t* status,
                     double* norm_mean, double* norm_stdev, uint32_t* ev_start, uint32_t* ev_length,

@@ -453,11 +453,11 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
     int4 q = make_int4(0, 0, 0, 0);
     if (slot < n_norm + a) {
       const int16_t* ptr = base_al + slot;
-      if (ptr + 8 <= raw_end) q = __ldg(reinterpret_cast<const int4*>(ptr));
+      if (ptr >= b.raw && ptr + 8 <= raw_end) q = __ldg(reinterpret_cast<const int4*>(ptr));
       else {
         int w[4] = {0, 0, 0, 0};
         for (int j = 0; j < 8; ++j)
-          if (ptr + j < raw_end) w[j >> 1] |= ((int)(unsigned short)ptr[j]) << (16 * (j & 1));
+          if (ptr + j >= b.raw && ptr + j < raw_end) w[j >> 1] |= ((int)(unsigned short)ptr[j]) << (16 * (j & 1));
         q = make_int4(w[0], w[1], w[2], w[3]);
       }
     }

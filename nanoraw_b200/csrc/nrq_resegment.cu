@@ -352,6 +352,21 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
   return splice_and_validate(c, n_bases, n_norm, region_samples);
 }
 
+// f-4: the running-difference trace plot_correction draws (plot_commands.py:225-229) for one window of an
+// already normalised signal: sequential float64 cumsum, then |2 cs[i+m] - cs[i] - cs[i+2m]|.  `cs` is
+// caller-provided scratch of n + 1 doubles.  One CTA; the window is a few hundred samples.
+__global__ void k_running_diffs(const double* __restrict__ sig, int n, int m, double* __restrict__ cs,
+                                double* __restrict__ out) {
+  if (threadIdx.x == 0) {
+    double acc = 0.0;
+    cs[0] = 0.0;
+    for (int j = 0; j < n; ++j) { acc = __dadd_rn(acc, sig[j]); cs[j + 1] = acc; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n - 2 * m + 1; i += blockDim.x)
+    out[i] = fabs(__dsub_rn(__dsub_rn(__dmul_rn(2.0, cs[i + m]), cs[i]), cs[i + 2 * m]));
+}
+
 #ifndef NRQ_SEG_MINB
 #define NRQ_SEG_MINB 6
 #endif

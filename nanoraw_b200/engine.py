@@ -351,6 +351,20 @@ class ResquiggleEngine(object):
                             [tuple(int(v) for v in row[:3]) for row in grp]))
         return st, out
 
+    def running_diffs(self, norm_signal, min_seg_len=4):
+        """plot_commands.py:225-229: the running-difference trace of a normalised signal window."""
+        t = self.torch
+        sig = np.ascontiguousarray(norm_signal, dtype=np.float64)
+        n = len(sig)
+        n_out = max(n - 2 * min_seg_len + 1, 0)
+        with t.cuda.device(self.device):
+            d_sig = t.from_numpy(sig).to(self.device) if n else t.zeros(1, dtype=t.float64, device=self.device)
+            scratch = t.empty(n + 1, dtype=t.float64, device=self.device)
+            out = t.empty(max(n_out, 1), dtype=t.float64, device=self.device)
+            rc = self.lib.nrq_running_diffs(_ptr(d_sig), n, min_seg_len, _ptr(scratch), _ptr(out), self._stream())
+            _lib.check(rc, 'nrq_running_diffs')
+        return out.cpu().numpy()[:n_out]
+
     def event_stats(self, norm_signal, new_segs, compute_sd=True):
         """per-base mean / sd of an already normalised signal (resquiggle.py:62-64), numpy summation
         order, for ONE read.  -> (norm_mean, norm_stdev)."""

@@ -142,6 +142,13 @@ def get_indel_groups(
             for s, e, cpts, indels in groups]
 
 
+def running_differences(norm_signal, min_seg_len=4):
+    """The trace `plot_correction` draws under the signal (plot_commands.py:225-229): the same running
+    difference get_cpts ranks (resquiggle.py:239-243), for a window of normalised signal."""
+    from .engine import get_engine
+    return get_engine().running_diffs(norm_signal, min_seg_len)
+
+
 def _read_raw_inputs(fast5_fn, norm_type, basecall_group, subgroup):
     """what resquiggle_read pulls out of the FAST5 file (resquiggle.py:327-347)."""
     try:

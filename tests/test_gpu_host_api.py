@@ -226,3 +226,15 @@ def test_pa_normalisation_against_oracle():
                                        pore_model=model, event_means=ev_means, event_kmers=kmers)
     assert np.array_equal(got, want)
     assert tuple(float(v) for v in gsv) == tuple(float(v) for v in wsv)
+
+
+def test_running_difference_trace():
+    """f-4: plot_correction's trace (plot_commands.py:225-229) is bit-identical to numpy's"""
+    from nanoraw_b200 import resquiggle as rsq
+    from oracle import resquiggle_oracle as orc
+    case = [c for c in OK_CASES if 'norm_signal' in c.a][0]
+    for lo, width in ((0, 200), (137, 501), (50, 8), (10, 7)):
+        window = case.a['norm_signal'][lo:lo + width]
+        got = rsq.running_differences(window)
+        want = orc.running_diffs(window) if width >= 8 else np.zeros(0)
+        assert np.array_equal(got, want)
