@@ -235,7 +235,8 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, in
     __syncwarp();
     const double* cs = buf + 1;
     int res;
-    if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos);
+    if (nrd <= 32) res = select_cpts_regs<1>(c, cs, nrd, K, t0, outpos);
+    else if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos);
     else if (nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos);
     else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos);
     __syncwarp();
