@@ -361,8 +361,10 @@ def gpu_arm(args):
                             'gbs': gbs, 'frac': gbs / peak}
         dom = max(stages, key=lambda k: stages[k]['ms'])
         path_gbs = stage_bytes['path'] / (float(stage_ms.sum()) * 1e-3) / 1e9
+        traffic, traffic_src = measured_traffic(args, dom)
         roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': stages[dom]['gbs'], 'peak': peak,
-                    'unit': 'GB/s', 'frac': stages[dom]['frac'], 'traffic': None,
+                    'unit': 'GB/s', 'frac': stages[dom]['frac'], 'traffic': traffic,
+                    'traffic_source': traffic_src,
                     'peak_source': peak_src, 'share_of_step': stages[dom]['ms'] / float(stage_ms.sum()),
                     'stages': stages,
                     'path': {'algorithmic_bytes': stage_bytes['path'], 'achieved': path_gbs,
@@ -391,6 +393,19 @@ def gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measured_traffic(args, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture of this same workload (profiles/), or None when the workload differs."""
+    path = os.path.join(ROOT, 'profiles', 'r1h_traffic_100k.json')
+    if not (os.path.exists(path) and args.reads == 100_000 and args.config == 'standard'):
+        return None, None
+    data = json.load(open(path))['kernels']
+    names = {'k_align_scan': ('k_align_count', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
+             'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}[kernel]
+    total = sum(data[n]['dram_read_bytes'] + data[n]['dram_write_bytes'] for n in names)
+    return int(total), 'profiles/r1h_traffic_100k.json (ncu --set full, same workload)'
 
 
 def algorithmic_bytes(t):
