@@ -471,7 +471,7 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
 
 def cpu_baseline_leg(args, reads):
     cores = host_cores()
-    n = min(len(reads), max(8, 2 * cores if args.cpu_reads is None else args.cpu_reads))
+    n = min(len(reads), max(8, 8 * cores if args.cpu_reads is None else args.cpu_reads))
     value, dt, samples, cpu_s = time_oracle(reads[:n], cores)
     return {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
             'sample': '%d reads of the same workload (%d samples), %.1f s wall, %.1f CPU-s; oracle port '
