@@ -114,3 +114,128 @@ def shard_bounds(raw_off, rank, world):
     for k in range(1, world + 1):
         cuts[k] = max(cuts[k], cuts[k - 1])
     return cuts[rank], cuts[rank + 1]
+
+
+class PinnedBatcher(object):
+    """Grow-only page-locked staging for device batches (north_star subsystem (a)).
+
+    Reads are appended straight into pinned ragged CSR buffers -- no per-batch allocation and no
+    second copy -- then handed to nrq_resquiggle_batch_host, whose results land in pinned output
+    buffers owned here.  Views returned by ``results`` stay valid until the next ``reset``.
+    Without CUDA (CPU tests of the packing logic) ordinary numpy memory is used.
+    """
+    IN = (('raw', np.int16), ('starts', np.int32), ('read_align', np.uint8), ('genome_align', np.uint8))
+    OUT = (('norm_mean', np.float64, 1), ('norm_stdev', np.float64, 1), ('ev_start', np.uint32, 1),
+           ('ev_length', np.uint32, 1), ('ev_base', np.uint8, 1))
+
+    def __init__(self, max_reads=512, raw_capacity=1 << 26, pinned=True):
+        self._pinned = pinned
+        self._keep = {}
+        self.max_reads = 0
+        self._cap = {'raw': 0, 'starts': 0, 'align': 0}
+        self._grow_reads(max_reads)
+        self._grow('raw', raw_capacity)
+        self._grow('starts', raw_capacity // 8)
+        self._grow('align', raw_capacity // 8)
+        self.reset()
+
+    # ---- storage
+    def _alloc(self, name, n, dtype):
+        n = max(int(n), 1)
+        if self._pinned:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.empty(n * np.dtype(dtype).itemsize, dtype=torch.uint8, pin_memory=True)
+                self._keep[name] = t
+                return t.numpy().view(dtype)
+        return np.empty(n, dtype=dtype)
+
+    def _regrow(self, name, n, dtype, used):
+        old = getattr(self, name, None)
+        new = self._alloc(name, n, dtype)
+        if old is not None and used:
+            new[:used] = old[:used]
+        setattr(self, name, new)
+
+    def _grow(self, kind, need):
+        cap = max(int(need), int(self._cap[kind] * 1.5))
+        used = {'raw': self._n_raw, 'starts': self._n_starts, 'align': self._n_align} \
+            if hasattr(self, '_n_raw') else {'raw': 0, 'starts': 0, 'align': 0}
+        if kind == 'raw':
+            self._regrow('raw', cap, np.int16, used['raw'])
+        elif kind == 'starts':
+            self._regrow('starts', cap, np.int32, used['starts'])
+        else:
+            self._regrow('read_align', cap, np.uint8, used['align'])
+            self._regrow('genome_align', cap, np.uint8, used['align'])
+            self._regrow('new_segs', cap + self.max_reads + 1, np.int32, 0)
+            for name, dt, _ in self.OUT:
+                self._regrow(name, cap, dt, 0)
+        self._cap[kind] = cap
+
+    def _grow_reads(self, need):
+        n = max(int(need), int(self.max_reads * 1.5))
+        used = getattr(self, 'n_reads', 0)
+        for name in ('raw_off', 'starts_off', 'align_off'):
+            self._regrow(name, n + 1, np.int64, used + 1 if used else 0)
+        self._regrow('read_start', n, np.int32, used)
+        self._regrow('scale_values_in', 4 * n, np.float64, 4 * used)
+        for name in ('status', 'n_bases', 'n_indels', 'region_samples'):
+            self._regrow(name, n, np.int32, 0)
+        self._regrow('scale_values', 4 * n, np.float64, 0)
+        self.max_reads = n
+        if self._cap['align']:
+            self._regrow('new_segs', self._cap['align'] + n + 1, np.int32, 0)
+
+    # ---- packing
+    def reset(self):
+        self.n_reads = 0
+        self._n_raw = self._n_starts = self._n_align = 0
+        self.raw_off[0] = self.starts_off[0] = self.align_off[0] = 0
+        self.has_given = False
+
+    @property
+    def total_align(self):
+        return self._n_align
+
+    def add(self, raw, read_start, starts, read_row, genome_row, given=None):
+        """append one read; returns its index in the batch"""
+        raw = np.asarray(raw)
+        starts = np.asarray(starts)
+        ra = np.frombuffer(read_row, dtype=np.uint8) if isinstance(read_row, (bytes, bytearray)) \
+            else np.asarray(read_row, dtype=np.uint8)
+        ga = np.frombuffer(genome_row, dtype=np.uint8) if isinstance(genome_row, (bytes, bytearray)) \
+            else np.asarray(genome_row, dtype=np.uint8)
+        if len(ra) != len(ga):
+            raise ValueError('alignment rows differ in length')
+        if len(starts) and int(starts[-1]) > np.iinfo(np.int32).max:
+            raise ValueError('read longer than 2^31 samples')
+        r = self.n_reads
+        if r + 1 > self.max_reads:
+            self._grow_reads(r + 1)
+        if self._n_raw + len(raw) > self._cap['raw']:
+            self._grow('raw', self._n_raw + len(raw))
+        if self._n_starts + len(starts) > self._cap['starts']:
+            self._grow('starts', self._n_starts + len(starts))
+        if self._n_align + len(ra) > self._cap['align']:
+            self._grow('align', self._n_align + len(ra))
+        self.raw[self._n_raw:self._n_raw + len(raw)] = raw
+        self.starts[self._n_starts:self._n_starts + len(starts)] = starts
+        self.read_align[self._n_align:self._n_align + len(ra)] = ra
+        self.genome_align[self._n_align:self._n_align + len(ga)] = ga
+        self._n_raw += len(raw)
+        self._n_starts += len(starts)
+        self._n_align += len(ra)
+        self.raw_off[r + 1] = self._n_raw
+        self.starts_off[r + 1] = self._n_starts
+        self.align_off[r + 1] = self._n_align
+        self.read_start[r] = read_start
+        if given is not None:
+            self.scale_values_in[4 * r:4 * r + 4] = (given[0], given[1], np.nan, np.nan) \
+                if len(given) == 2 else given
+            self.has_given = True
+        self.n_reads = r + 1
+        return r
+
+    def input_bytes(self):
+        return 2 * self._n_raw + 4 * self._n_starts + 2 * self._n_align + 28 * self.n_reads

@@ -446,7 +446,8 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     o.ev_length = (uint32_t*)up(nullptr, 4 * (size_t)n_align);
     o.ev_base = (uint8_t*)up(nullptr, (size_t)n_align);
     o.region_samples = (int32_t*)up(nullptr, 4 * (size_t)n);
-    int64_t ws_bytes = nrq_workspace_bytes(n, n_align, p);
+    // worst case: every alignment column starts an indel run, so no read can hit NRQ_ST_WORKSPACE here
+    int64_t ws_bytes = carve(nullptr, n, n_align, p, n_align + n + 64).bytes + 2048;
     void* ws = up(nullptr, (size_t)ws_bytes);
     if (err != cudaSuccess) break;
     rc = nrq_resquiggle_batch(&d, p, &o, ws, ws_bytes, s);

@@ -232,9 +232,64 @@ class ResquiggleEngine(object):
         arrays['scale_values'] = arrays['scale_values'][:4 * R]
         return HostResults(dbatch.host.align_off, arrays)
 
+    # ---- host buffers in, host buffers out: the C-ABI host entry point (chunked, multi-stream)
+    def _host_handle(self):
+        if getattr(self, '_handle', None) is None:
+            import atexit
+            h = self.lib.nrq_create(self.device.index or 0)
+            if not h:
+                raise _lib.NrqError('nrq_create failed: ' + self.lib.nrq_last_error().decode())
+            self._handle = h
+            atexit.register(self._release_handle)
+        return self._handle
+
+    def _release_handle(self):
+        h, self._handle = getattr(self, '_handle', None), None
+        if h:
+            self.lib.nrq_destroy(h)
+
+    def run_host(self, src, params):
+        """Run a batch whose CSR arrays live in host memory (a ReadBatch or a PinnedBatcher) through
+        nrq_resquiggle_batch_host.  Results are numpy arrays: views of the batcher's pinned output
+        buffers (valid until its next reset) or fresh arrays for a ReadBatch."""
+        R, A = src.n_reads, src.total_align
+        pc = params.to_c() if isinstance(params, ResquiggleParams) else params
+        hb = _lib.NrqBatch()
+        hb.n_reads = R
+        keep = []
+        for name in ReadBatch.FIELDS:
+            arr = np.ascontiguousarray(getattr(src, name))
+            keep.append(arr)
+            setattr(hb, name, arr.ctypes.data)
+        sv_in = getattr(src, 'scale_values_in', None)
+        if sv_in is not None and (getattr(src, 'has_given', True)):
+            sv_in = np.ascontiguousarray(sv_in, dtype=np.float64)
+            keep.append(sv_in)
+            hb.scale_values_in = sv_in.ctypes.data
+        outs = {}
+        shapes = {'status': (R, np.int32), 'n_bases': (R, np.int32), 'n_indels': (R, np.int32),
+                  'region_samples': (R, np.int32), 'scale_values': (4 * R, np.float64),
+                  'new_segs': (A + R, np.int32), 'norm_mean': (A, np.float64),
+                  'norm_stdev': (A, np.float64), 'ev_start': (A, np.uint32), 'ev_length': (A, np.uint32),
+                  'ev_base': (A, np.uint8)}
+        hr = _lib.NrqResults()
+        own = hasattr(src, 'reset')  # a PinnedBatcher brings its own output buffers
+        for name, (n, dt) in shapes.items():
+            arr = getattr(src, name)[:max(n, 1)] if own else np.empty(max(n, 1), dtype=dt)
+            outs[name] = arr[:n]
+            setattr(hr, name, arr.ctypes.data)
+        if R:
+            rc = self.lib.nrq_resquiggle_batch_host(self._host_handle(), C.byref(hb), C.byref(pc), C.byref(hr))
+            _lib.check(rc, 'nrq_resquiggle_batch_host')
+        return HostResults(np.asarray(src.align_off[:R + 1]), outs)
+
     def run(self, batch, params):
-        """Host arrays in, host arrays out.  Reads the indel workspace could not hold are
-        re-run once with a workspace sized for the worst case."""
+        """Host arrays in, host arrays out (ReadBatch -> HostResults)."""
+        return self.run_host(batch, params)
+
+    def run_via_torch(self, batch, params):
+        """Same through torch-managed device tensors and nrq_resquiggle_batch.  Reads the indel
+        workspace could not hold are re-run once with a workspace sized for the worst case."""
         db = self.upload(batch)
         pc = params.to_c()
         out = self.run_device(db, pc)

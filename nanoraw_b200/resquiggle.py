@@ -168,6 +168,17 @@ def _read_raw_inputs(fast5_fn, norm_type, basecall_group, subgroup):
     return channel_info, all_raw_signal, event_means, event_kmers
 
 
+_BATCHER = []
+
+
+def _batcher():
+    """the worker process's pinned staging buffers (grow-only, reused for every device batch)"""
+    if not _BATCHER:
+        from .batch import PinnedBatcher
+        _BATCHER.append(PinnedBatcher(max_reads=DEVICE_BATCH_READS))
+    return _BATCHER[0]
+
+
 class _PendingRead(object):
     __slots__ = ('fast5_fn', 'alignVals', 'genome_loc', 'starts', 'read_start', 'read_info',
                  'raw', 'given', 'rows')
@@ -188,7 +199,6 @@ def resquiggle_reads_batch(
     """The batched body of resquiggle_read (resquiggle.py:318-401) for a list of _PendingRead:
     FAST5 read -> one device batch (a1..a7) -> FAST5 write.  Returns [(error string, read)] for
     the reads that failed, with the reference's messages."""
-    from .batch import ReadBatch
     from .engine import ResquiggleParams, get_engine
     failed = []
     ready = []
@@ -203,19 +213,17 @@ def resquiggle_reads_batch(
             failed.append((str(e), pr))
     if not ready:
         return failed
-    sv_in = None
-    if norm_type != 'median':
-        sv_in = np.array([[float(pr.given[0]), float(pr.given[1]), np.nan, np.nan] for pr in ready])
-    batch = ReadBatch.from_arrays(
-        [pr.raw for pr in ready], [int(pr.read_start) for pr in ready],
-        [np.asarray(pr.starts) for pr in ready],
-        [pr.rows[0].encode() for pr in ready], [pr.rows[1].encode() for pr in ready], sv_in)
     engine = engine or get_engine()
+    batcher = _batcher()
+    batcher.reset()
+    for pr in ready:  # straight into pinned CSR staging: no intermediate copies
+        batcher.add(pr.raw, int(pr.read_start), pr.starts, pr.rows[0].encode(), pr.rows[1].encode(),
+                    None if norm_type == 'median' else (float(pr.given[0]), float(pr.given[1])))
     params = ResquiggleParams(
         norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=outlier_thresh,
         compute_sd=compute_sd, num_cpts_limit=num_cpts_limit, timeout=timeout,
         min_event_obs=min_event_obs)
-    res = engine.run(batch, params)
+    res = engine.run_host(batcher, params)
     for r, pr in enumerate(ready):
         exc = exception_for(res.status[r])
         if exc is not None:

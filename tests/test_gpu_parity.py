@@ -241,3 +241,24 @@ def test_host_buffer_entry_point(engine, chunk_bytes, monkeypatch):
         assert np.array_equal(outs['ev_base'][o:o + n], want.ev_base[o:o + n])
         assert np.array_equal(outs['ev_start'][o:o + n], want.ev_start[o:o + n])
 
+
+
+def test_host_path_equals_torch_path_and_pinned_batcher(engine):
+    """engine.run (C-ABI host entry point) == the torch-tensor route == a PinnedBatcher fed read by read"""
+    from nanoraw_b200.batch import PinnedBatcher
+    from nanoraw_b200.engine import ResquiggleParams
+    reads = synth.make_reads(9, synth.config_short(48000), genome=synth.make_genome(200_000, seed=9))
+    batch = ReadBatch.from_reads(reads)
+    params = ResquiggleParams()
+    a = engine.run(batch, params)
+    b = engine.run_via_torch(batch, params)
+    pb = PinnedBatcher(max_reads=4, raw_capacity=10_000)
+    for rd in reads:
+        pb.add(rd.raw, rd.read_start_rel_to_raw, rd.starts, rd.read_align, rd.genome_align)
+    c = engine.run_host(pb, params)
+    for other in (b, c):
+        assert np.array_equal(a.status, other.status) and np.array_equal(a.n_bases, other.n_bases)
+        assert np.array_equal(a.scale_values, other.scale_values, equal_nan=True)
+        for r in range(len(reads)):
+            assert np.array_equal(a.new_segs_of(r), other.new_segs_of(r))
+            assert np.array_equal(a.events_of(r), other.events_of(r))

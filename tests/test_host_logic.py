@@ -120,3 +120,23 @@ def test_status_exception_mapping():
     assert isinstance(exception_for(_lib.ST_FPE_DIVIDE), FloatingPointError)
     assert error_string(_lib.ST_CPTS_LIMIT) == \
         'RuntimeError: Reached maximum number of changepoints for a single indel'
+
+
+def test_pinned_batcher_packs_like_readbatch_and_grows():
+    from nanoraw_b200.batch import PinnedBatcher
+    cfg = synth.SynthConfig(span_mean=150, span_sd=30, seed_base=971)
+    reads = synth.make_reads(9, cfg, genome=synth.make_genome(20_000, seed=2))
+    pb = PinnedBatcher(max_reads=2, raw_capacity=500, pinned=False)   # forces every buffer to grow
+    for rd in reads:
+        pb.add(rd.raw, rd.read_start_rel_to_raw, rd.starts, rd.read_align, rd.genome_align)
+    want = ReadBatch.from_reads(reads)
+    assert pb.n_reads == want.n_reads and pb.total_align == want.total_align
+    for f in ReadBatch.FIELDS:
+        n = len(getattr(want, f))
+        assert np.array_equal(getattr(pb, f)[:n], getattr(want, f)), f
+    pb.reset()
+    assert pb.n_reads == 0 and pb.total_align == 0
+    pb.add(reads[3].raw, 5, reads[3].starts, reads[3].read_align, reads[3].genome_align, given=(1.5, 2.0))
+    assert pb.has_given and pb.scale_values_in[0] == 1.5 and np.isnan(pb.scale_values_in[2])
+    with pytest.raises(ValueError):
+        pb.add(reads[0].raw, 0, reads[0].starts, b'AC', b'A')
