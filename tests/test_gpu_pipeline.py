@@ -1,0 +1,123 @@
+"""Front end -> queue -> GPU re-squiggle worker -> FAST5 write, in one process: basecalled FAST5 files
+(in-memory backend) + a stand-in mapper that replays SAM records -> RawGenomeCorrected groups, checked
+against the oracle run on the inputs the front end produced."""
+import json
+import os
+import queue
+import sys
+
+import numpy as np
+import pytest
+
+from nanoraw_b200 import fast5_io, synth
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FAKE_BWA = os.path.join(HERE, 'tools', 'fake_bwa.py')
+
+
+def make_basecalled_fast5(name, read, events, start_time=0):
+    f = fast5_io.MemFile(name, 'w')
+    rd = f.create_group('Raw/Reads/Read_3')
+    rd.create_dataset('Signal', data=read.raw)
+    rd.attrs['read_id'] = read.read_id
+    rd.attrs['start_time'] = np.uint64(start_time)
+    ch = f.create_group('UniqueGlobalKey/channel_id')
+    for k, v in (('offset', 10.0), ('range', 1400.0), ('digitisation', 8192.0), ('sampling_rate', 4000.0)):
+        ch.attrs[k] = np.float64(v)
+    ch.attrs['channel_number'] = '11'
+    grp = f.create_group('Analyses/Basecall_1D_000')
+    grp.attrs['version'] = '1.1.0'
+    f.create_group('Analyses/Basecall_1D_000/BaseCalled_template').create_dataset('Events', data=events)
+    f.close()
+
+
+def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch):
+    from nanoraw_b200 import frontend
+    from nanoraw_b200 import resquiggle as rsq
+    from oracle import resquiggle_oracle as orc
+
+    cfg = synth.SynthConfig(span_mean=900, span_sd=150, seed_base=71000)
+    genome = synth.make_genome(120_000, seed=23)
+    genome_fa = tmp_path / 'genome.fa'
+    genome_fa.write_text('>synth_chr1 test genome\n' + genome.tobytes().decode() + '\n')
+    n_reads = 12
+    records, names, reads = {}, [], []
+    for i in range(n_reads):
+        read = synth.make_read(genome, synth.kmer_levels(cfg), cfg, i)
+        # the basecaller saw a few extra bases each side that the mapper soft-clips
+        clip = (i % 3, (2 * i) % 5)
+        events = synth.to_basecall_events(read, stay_rate=0.12, clip_bases=clip, seed=i)
+        name = 'mem://pipeline/read_%02d.fast5' % i
+        # samples taken by the clipped leading bases (a base starts at every moving event)
+        base_events = np.flatnonzero(events['move'] == 1)
+        lead = int(np.round(events['start'][base_events[clip[0]]] * 4000.0))
+        # the clipped bases sit just before the read's own signal inside the raw array
+        shifted = events.copy()
+        shifted['start'] = events['start'] + (read.read_start_rel_to_raw - lead) / 4000.0
+        assert read.read_start_rel_to_raw - lead >= 0
+        make_basecalled_fast5(name, read, shifted)
+        rec = synth.to_sam_record(read, soft_clip=clip, seed=i)
+        records[('BaseCalled_template:::' + name).replace(' ', '|||')] = rec
+        names.append(name)
+        reads.append(read)
+    # one file with no alignment, one file without basecalls
+    unaligned = 'mem://pipeline/unaligned.fast5'
+    extra = synth.make_read(genome, synth.kmer_levels(cfg), cfg, 99)
+    make_basecalled_fast5(unaligned, extra, synth.to_basecall_events(extra, seed=99))
+    rec_path = tmp_path / 'records.json'
+    rec_path.write_text(json.dumps(records))
+    monkeypatch.setenv('FAKE_BWA_RECORDS', str(rec_path))
+    mapper = tmp_path / 'bwa'
+    mapper.write_text('#!/bin/sh\nexec %s %s "$@"\n' % (sys.executable, FAKE_BWA))
+    mapper.chmod(0o755)
+
+    fast5_q, basecalls_q, failed_q = queue.Queue(), queue.Queue(), queue.Queue()
+    fast5_q.put(names[:7] + [unaligned])
+    fast5_q.put(names[7:])
+    frontend.alignment_worker(fast5_q, basecalls_q, failed_q, str(genome_fa), str(mapper), 'bwa_mem',
+                              'Basecall_1D_000', ['BaseCalled_template'], 'RawGenomeCorrected_000', False, 1)
+    items = []
+    while not basecalls_q.empty():
+        items.append(basecalls_q.get())
+    assert len(items) == len(names)
+    for it in items:
+        basecalls_q.put(it)
+    basecalls_q.put((None, None))
+    rsq.resquiggle_worker(basecalls_q, failed_q, 'Basecall_1D_000', 'RawGenomeCorrected_000', 'median', 5,
+                          None, None, True, None)
+    failures = {}
+    while not failed_q.empty():
+        err, rid = failed_q.get()
+        failures[rid] = err
+    assert failures == {'BaseCalled_template:::' + unaligned:
+                        'Alignment not produced. Potentially failed to locate BWA index files.'}
+
+    by_name = dict(items)
+    for name, read in zip(names, reads):
+        (rows, loc, starts, read_start, info), = by_name[name]
+        assert rows[0].encode() == read.read_align and rows[1].encode() == read.genome_align
+        assert loc.Strand == read.strand and loc.Start == read.genome_start
+        want = orc.resquiggle_read(read.raw, int(read_start), starts, rows[0], rows[1])
+        sub = fast5_io.MemFile(name)['/Analyses/RawGenomeCorrected_000/BaseCalled_template']
+        ev = sub['Events'][()]
+        assert np.array_equal(ev['start'], want['events']['start'])
+        assert np.array_equal(ev['length'], want['events']['length'])
+        assert np.array_equal(ev['base'], want['events']['base'])
+        assert np.max(np.abs(ev['norm_mean'] - want['events']['norm_mean'])) < 1e-9
+        assert sub.attrs['shift'] == float(want['scale_values'].shift)
+        assert sub.attrs['scale'] == float(want['scale_values'].scale)
+        assert sub['Alignment'].attrs['mapped_start'] == read.genome_start
+        assert sub['Alignment'].attrs['clipped_bases_start'] == info.ClipStart
+        assert np.array_equal(sub['Alignment/read_segments'][()], starts)
+        assert sub['Events'].attrs['read_start_rel_to_raw'] == read_start
+    # second run without --overwrite: every file is skipped (resume semantics of prep_fast5)
+    fast5_q.put(names)
+    frontend.alignment_worker(fast5_q, basecalls_q, failed_q, str(genome_fa), str(mapper), 'bwa_mem',
+                              'Basecall_1D_000', ['BaseCalled_template'], 'RawGenomeCorrected_000', False, 1)
+    assert basecalls_q.empty()
+    skipped = [failed_q.get() for _ in range(failed_q.qsize())]
+    assert len(skipped) == len(names)
+    assert all(e == 'Raw genome corrected data exists for this read and --overwrite is not set.'
+               for e, _ in skipped)
