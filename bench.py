@@ -441,10 +441,12 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
         t = pinned(getattr(host_batch, f))
         h2d += t.numel() * t.element_size()
         setattr(hb, f, t.data_ptr())
+    # what resquiggle_read hands to the FAST5 writer: scale values + the event table (+ status); new_segs is
+    # start/length again and region_samples is an accounting aid, so neither is copied back
     outs = {'status': (R, np.int32), 'n_bases': (R, np.int32), 'n_indels': (R, np.int32),
-            'scale_values': (4 * R, np.float64), 'new_segs': (A + R, np.int32),
+            'scale_values': (4 * R, np.float64),
             'norm_mean': (A, np.float64), 'norm_stdev': (A, np.float64), 'ev_start': (A, np.uint32),
-            'ev_length': (A, np.uint32), 'ev_base': (A, np.uint8), 'region_samples': (R, np.int32)}
+            'ev_length': (A, np.uint32), 'ev_base': (A, np.uint8)}
     hr = _lib.NrqResults()
     d2h = 0
     host_out = {}

@@ -302,7 +302,10 @@ int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const 
 // The batch is cut into chunks of reads that flow through kSlots independent (stream, device buffers) sets:
 // chunk c+1's host->device copies overlap chunk c's kernels and chunk c-1's device->host copies, and the two
 // PCIe directions run concurrently.  Per-chunk CSR offsets are rebased on the host into pinned staging.
-constexpr int kSlots = 3;
+#ifndef NRQ_HOST_SLOTS
+#define NRQ_HOST_SLOTS 3
+#endif
+constexpr int kSlots = NRQ_HOST_SLOTS;
 constexpr int64_t kChunkBytesDefault = 96ll << 20;  // target input bytes per chunk (NRQ_HOST_CHUNK_BYTES overrides)
 
 struct nrq_slot {
