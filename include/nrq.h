@@ -168,6 +168,18 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
                     double* norm_mean, double* norm_stdev, uint32_t* ev_start, uint32_t* ev_length,
                     uint8_t* ev_base, void* stream);
 
+/* f-3 (downstream of the hot path): genome-anchored aggregation of corrected event tables, the arithmetic of
+ * get_coverage / get_base_means / get_base_sds / get_base_lengths (nanoraw_helper.py:298-444), for ONE
+ * (chromosome, strand) track.  The track's reads must be sorted by mapped start; read k covers genome positions
+ * [read_start[k], read_start[k] + read_len[k]), its event rows start at ev_off[k] in the three event arrays and
+ * are taken in reverse order when read_rev[k] != 0.  max_len >= every read_len.  Outputs have track_len entries;
+ * the means are NaN where coverage is 0.  All pointers are device pointers. */
+int nrq_genome_aggregate(const int32_t* read_start, const int32_t* read_len, const int64_t* ev_off,
+                         const uint8_t* read_rev, int32_t n_track_reads, int32_t max_len, int32_t track_len,
+                         const double* norm_mean, const double* norm_stdev, const uint32_t* ev_length,
+                         int32_t* coverage, double* mean_of_means, double* mean_of_sds, double* mean_of_lengths,
+                         void* stream);
+
 /* The whole path a1..a7 for a batch resident in device memory (the body of resquiggle_worker's loop,
  * resquiggle.py:424-433, minus FAST5 I/O).  workspace: device, >= nrq_workspace_bytes(). */
 int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_results* out,

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 LIB = os.path.join(PKG, 'libnrq.so')
-SOURCES = ['nrq_api.cu', 'nrq_indels.cu', 'nrq_norm.cu', 'nrq_resegment.cu', 'nrq_events.cu',
+SOURCES = ['nrq_api.cu', 'nrq_indels.cu', 'nrq_norm.cu', 'nrq_resegment.cu', 'nrq_events.cu', 'nrq_aggregate.cu',
            'nrq_common.cuh', os.path.join('..', '..', 'include', 'nrq.h')]
 
 NVCC_FLAGS = [

@@ -11,6 +11,7 @@
 #include "nrq_norm.cu"
 #include "nrq_resegment.cu"
 #include "nrq_events.cu"
+#include "nrq_aggregate.cu"
 
 namespace {
 
@@ -215,6 +216,24 @@ int nrq_running_diffs(const double* signal, int32_t n, int32_t min_seg_len, doub
   if (n - 2 * min_seg_len + 1 <= 0) return 0;
   nrq::k_running_diffs<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(signal, n, min_seg_len, scratch, out);
   NRQ_CHECK_LAUNCH("k_running_diffs");
+  return 0;
+}
+
+int nrq_genome_aggregate(const int32_t* read_start, const int32_t* read_len, const int64_t* ev_off,
+                         const uint8_t* read_rev, int32_t n_track_reads, int32_t max_len, int32_t track_len,
+                         const double* norm_mean, const double* norm_stdev, const uint32_t* ev_length,
+                         int32_t* coverage, double* mean_of_means, double* mean_of_sds, double* mean_of_lengths,
+                         void* stream) {
+  if (!coverage || !mean_of_means || !mean_of_sds || !mean_of_lengths)
+    return fail("nrq_genome_aggregate: NULL output");
+  if (n_track_reads > 0 && (!read_start || !read_len || !ev_off || !read_rev || !norm_mean || !norm_stdev ||
+                            !ev_length))
+    return fail("nrq_genome_aggregate: NULL input");
+  if (track_len <= 0) return 0;
+  nrq::k_genome_aggregate<<<(track_len + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      read_start, read_len, ev_off, read_rev, n_track_reads, max_len, track_len, norm_mean, norm_stdev, ev_length,
+      coverage, mean_of_means, mean_of_sds, mean_of_lengths);
+  NRQ_CHECK_LAUNCH("k_genome_aggregate");
   return 0;
 }
 

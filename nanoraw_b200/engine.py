@@ -406,6 +406,38 @@ class ResquiggleEngine(object):
                             [tuple(int(v) for v in row[:3]) for row in grp]))
         return st, out
 
+    def genome_aggregate(self, starts, lengths, reverse, means, sds, ev_lengths, track_len):
+        """One (chromosome, strand) track of get_coverage / get_base_means / get_base_sds / get_base_lengths
+        (nanoraw_helper.py:298-444).  starts / lengths / reverse: per read; means / sds / ev_lengths: per-read
+        event columns (lists of arrays).  -> (coverage int32[L], mean of means, mean of sds, mean of lengths)."""
+        t = self.torch
+        L = int(track_len)
+        order = np.argsort(np.asarray(starts), kind='stable')
+        n_reads = len(order)
+        st = np.asarray(starts, dtype=np.int32)[order]
+        ln = np.asarray(lengths, dtype=np.int32)[order]
+        rv = np.asarray(reverse, dtype=np.uint8)[order]
+        off = np.zeros(n_reads + 1, dtype=np.int64)
+        np.cumsum(ln, out=off[1:])
+        cat = lambda cols, dt: (np.concatenate([np.asarray(cols[i], dtype=dt) for i in order])
+                                if n_reads else np.zeros(1, dt))
+        with t.cuda.device(self.device):
+            dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            d_st, d_ln, d_rv, d_off = dev(st if n_reads else np.zeros(1, np.int32)), \
+                dev(ln if n_reads else np.zeros(1, np.int32)), dev(rv if n_reads else np.zeros(1, np.uint8)), \
+                dev(off[:-1] if n_reads else np.zeros(1, np.int64))
+            d_m, d_s = dev(cat(means, np.float64)), dev(cat(sds, np.float64))
+            d_l = dev(cat(ev_lengths, np.uint32).view(np.int32))
+            cov = t.empty(max(L, 1), dtype=t.int32, device=self.device)
+            o_m = t.empty(max(L, 1), dtype=t.float64, device=self.device)
+            o_s = t.empty(max(L, 1), dtype=t.float64, device=self.device)
+            o_l = t.empty(max(L, 1), dtype=t.float64, device=self.device)
+            rc = self.lib.nrq_genome_aggregate(
+                _ptr(d_st), _ptr(d_ln), _ptr(d_off), _ptr(d_rv), n_reads, int(ln.max()) if n_reads else 0, L,
+                _ptr(d_m), _ptr(d_s), _ptr(d_l), _ptr(cov), _ptr(o_m), _ptr(o_s), _ptr(o_l), self._stream())
+            _lib.check(rc, 'nrq_genome_aggregate')
+        return (cov.cpu().numpy()[:L], o_m.cpu().numpy()[:L], o_s.cpu().numpy()[:L], o_l.cpu().numpy()[:L])
+
     def running_diffs(self, norm_signal, min_seg_len=4):
         """plot_commands.py:225-229: the running-difference trace of a normalised signal window."""
         t = self.torch

@@ -162,3 +162,113 @@ def parse_fasta(fasta_fn):
     if cur_id is not None and chunks:
         records[cur_id] = ''.join(chunks)
     return records
+
+
+# ------------------------------------------------------------------------------------------
+# f-3: corrected-read index and genome-anchored aggregation (nanoraw_helper.py:15-17, 110-152, 298-444).
+# The per-position arithmetic runs on the GPU (nrq_genome_aggregate); reading the Events back from
+# the FAST5 files stays on the host, as in the reference.
+readData = namedtuple('readData', (
+    'start', 'end', 'segs', 'read_start_rel_to_raw', 'strand', 'fn', 'corr_group'))
+
+
+def parse_fast5s(files, corrected_group, basecall_subgroups):
+    """nanoraw_helper.py:110-152 -> {(chrom, strand): [readData]} for every corrected read found."""
+    import sys
+    from collections import defaultdict
+    from . import fast5_io
+    raw_read_coverage = defaultdict(list)
+    for read_fn in files:
+        for subgroup in basecall_subgroups:
+            try:
+                read_data = fast5_io.open_fast5(read_fn, 'r')
+            except IOError:
+                continue  # probably a truncated file
+            slot = '/'.join(('/Analyses', corrected_group, subgroup))
+            if slot not in read_data:
+                continue
+            corr = read_data[slot]
+            try:
+                align = dict(corr['Alignment'].attrs.items())
+                read_start_rel_to_raw = corr['Events'].attrs['read_start_rel_to_raw']
+                events = fast5_io.read_dataset(corr['Events'])
+                events_end = events[-1]['start'] + events[-1]['length']
+                segs = np.concatenate([events['start'], [events_end, ]])
+            except Exception:
+                sys.stderr.write('********** WARNING: Corrupted corrected events in ' +
+                                 read_fn + '. ********\n')
+                continue
+            raw_read_coverage[(align['mapped_chrom'], align['mapped_strand'])].append(readData(
+                align['mapped_start'], align['mapped_start'] + len(segs) - 1, segs,
+                read_start_rel_to_raw, align['mapped_strand'], read_fn,
+                corrected_group + '/' + subgroup))
+            read_data.close()
+    return raw_read_coverage
+
+
+def _read_event_columns(r_data):
+    from . import fast5_io
+    try:
+        read_data = fast5_io.open_fast5(r_data.fn, 'r')
+    except IOError:
+        return None
+    slot = '/'.join(('/Analyses', r_data.corr_group, 'Events'))
+    if slot not in read_data:
+        return None
+    events = fast5_io.read_dataset(read_data[slot])
+    return events['norm_mean'], events['norm_stdev'], events['length']
+
+
+def get_base_stats(raw_read_coverage, chrm_sizes):
+    """One pass over the corrected reads -> (coverage, mean of norm_mean, mean of norm_stdev, mean of length),
+    each a {(chrom, strand): array of chromosome length}.  Additive helper: the three reference functions
+    below re-open every FAST5 file once each; this reads them once and aggregates on the GPU."""
+    from .engine import get_engine
+    engine = get_engine()
+    out = ({}, {}, {}, {})
+    for chrm in chrm_sizes.keys():
+        for strand in ('+', '-'):
+            reads = raw_read_coverage.get((chrm, strand), [])
+            starts, cols = [], []
+            for r_data in reads:
+                c = _read_event_columns(r_data)
+                if c is None:
+                    continue
+                starts.append(r_data.start)
+                cols.append(c)
+            res = engine.genome_aggregate(
+                starts, [len(c[0]) for c in cols], [strand == '-'] * len(cols),
+                [c[0] for c in cols], [c[1] for c in cols], [c[2] for c in cols], chrm_sizes[chrm])
+            for d, arr in zip(out, res):
+                d[(chrm, strand)] = arr
+    return out
+
+
+def get_coverage(raw_read_coverage):
+    """nanoraw_helper.py:298-308: coverage over [start, end) of every read, up to the largest end."""
+    from .engine import get_engine
+    engine = get_engine()
+    read_coverage = {}
+    for (chrm, strand), reads in raw_read_coverage.items():
+        max_end = max(r.end for r in reads)
+        lens = [r.end - r.start for r in reads]
+        zeros = [np.zeros(n) for n in lens]
+        cov = engine.genome_aggregate([r.start for r in reads], lens, [False] * len(reads), zeros, zeros,
+                                      [np.zeros(n, dtype=np.uint32) for n in lens], max_end)[0]
+        read_coverage[(chrm, strand)] = cov.astype(np.int_)
+    return read_coverage
+
+
+def get_base_means(raw_read_coverage, chrm_sizes):
+    """nanoraw_helper.py:342-361 (NaN where no read covers the base)"""
+    return get_base_stats(raw_read_coverage, chrm_sizes)[1]
+
+
+def get_base_sds(raw_read_coverage, chrm_sizes):
+    """nanoraw_helper.py:388-402"""
+    return get_base_stats(raw_read_coverage, chrm_sizes)[2]
+
+
+def get_base_lengths(raw_read_coverage, chrm_sizes):
+    """nanoraw_helper.py:430-444"""
+    return get_base_stats(raw_read_coverage, chrm_sizes)[3]
