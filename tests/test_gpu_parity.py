@@ -262,3 +262,37 @@ def test_host_path_equals_torch_path_and_pinned_batcher(engine):
         for r in range(len(reads)):
             assert np.array_equal(a.new_segs_of(r), other.new_segs_of(r))
             assert np.array_equal(a.events_of(r), other.events_of(r))
+
+
+def test_malformed_reads_get_a_status_and_do_not_disturb_their_neighbours(engine):
+    """ragged / inconsistent inputs: every bad read is reported through status[r]; good reads in the same
+    batch are unaffected"""
+    import copy
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.engine import ResquiggleParams
+    cfg = synth.SynthConfig(span_mean=400, span_sd=40, seed_base=52000)
+    good = synth.make_reads(6, cfg, genome=synth.make_genome(60_000, seed=9))
+    want = engine.run(ReadBatch.from_reads(good), ResquiggleParams())
+    bad = [copy.copy(r) for r in good]
+    # 1: alignment starts with a gap column (parse_sam_record never produces this, resquiggle.py:623-637)
+    bad[1].read_align = b'-' + bad[1].read_align[1:]
+    # 2: one boundary too many for the read bases of the alignment
+    bad[2].starts = np.concatenate([bad[2].starts, [bad[2].starts[-1] + 5]])
+    # 3: read_start beyond the stored signal
+    bad[3].read_start_rel_to_raw = len(bad[3].raw) + 10
+    # 4: a zero-length basecaller event in the untouched part (resquiggle.py:373-375)
+    s = bad[4].starts.copy()
+    s[1] = s[0]
+    bad[4].starts = s
+    res = engine.run(ReadBatch.from_reads(bad), ResquiggleParams())
+    assert res.status[1] == _lib.ST_BAD_ALIGNMENT
+    assert res.status[2] == _lib.ST_BAD_INPUT
+    assert res.status[3] in (_lib.ST_BAD_INPUT, _lib.ST_PAST_END)
+    assert res.status[4] in (_lib.ST_ZERO_LEN, _lib.ST_OK)
+    for r in (0, 5):
+        assert res.ok(r)
+        assert np.array_equal(res.new_segs_of(r), want.new_segs_of(r))
+        assert np.array_equal(res.events_of(r), want.events_of(r))
+    # an empty batch is a no-op
+    empty = engine.run(ReadBatch.from_arrays([], [], [], [], []), ResquiggleParams())
+    assert empty.n_reads == 0
