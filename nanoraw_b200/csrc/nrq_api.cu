@@ -318,18 +318,23 @@ int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const 
 }
 
 // ------------------------------------------------------------------ host-buffer entry point
-// The batch is cut into chunks of reads that flow through kSlots independent (stream, device buffers) sets:
-// chunk c+1's host->device copies overlap chunk c's kernels and chunk c-1's device->host copies, and the two
-// PCIe directions run concurrently.  Per-chunk CSR offsets are rebased on the host into pinned staging.
-#ifndef NRQ_HOST_SLOTS
-#define NRQ_HOST_SLOTS 3
-#endif
-constexpr int kSlots = NRQ_HOST_SLOTS;
-constexpr int64_t kChunkBytesDefault = 96ll << 20;  // target input bytes per chunk (NRQ_HOST_CHUNK_BYTES overrides)
+// The batch is cut into chunks of reads that flow through a three-stage pipeline: one host->device copy
+// stream, one kernel stream per slot, one device->host copy stream, chained by events.  Each PCIe direction is
+// a FIFO, so chunk c is on the device as early as possible, its kernels overlap chunk c+1's upload and chunk
+// c-1's download, and the two directions stay busy together.  A slot is a set of device buffers; a chunk may
+// reuse it once the slot's previous download has finished.  Per-chunk CSR offsets are rebased on the host into
+// pinned staging.
+constexpr int kMaxSlots = 8;
+constexpr int kSlotsDefault = 6;  // NRQ_HOST_SLOTS overrides (1..kMaxSlots), read at nrq_create
+// Input bytes per chunk: an eighth of the call, within [kChunkBytesMin, kChunkBytesMax]; NRQ_HOST_CHUNK_BYTES
+// forces a size.  A chunk's kernels take about 3 ms however small it is (K2 walks a read's indel groups one after
+// the other), so slots x chunk >= ~300 MB must be in flight to keep both PCIe directions busy, while a small
+// call still wants several chunks to overlap at all.  Measured sweep in profiles/README.md.
+constexpr int64_t kChunkBytesMin = 32ll << 20, kChunkBytesMax = 128ll << 20;
 
 struct nrq_slot {
-  cudaStream_t stream = nullptr;
-  cudaEvent_t done = nullptr;
+  cudaStream_t stream = nullptr;  // kernels
+  cudaEvent_t up_done = nullptr, k_done = nullptr, done = nullptr;
   std::vector<std::pair<void*, size_t>> dev;  // grow-only device buffers
   int64_t* off_stage = nullptr;               // pinned: 3 rebased offset arrays
   size_t off_stage_elems = 0;
@@ -337,7 +342,9 @@ struct nrq_slot {
 
 struct nrq_handle {
   int device;
-  nrq_slot slots[kSlots];
+  int n_slots = kSlotsDefault;
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  nrq_slot slots[kMaxSlots];
 };
 
 static void* dev_buf(nrq_slot& sl, size_t idx, size_t bytes, cudaError_t* err) {
@@ -357,8 +364,17 @@ nrq_handle* nrq_create(int32_t device) {
   if (cudaSetDevice(device) != cudaSuccess) { fail("nrq_create: cudaSetDevice failed"); return nullptr; }
   nrq_handle* h = new nrq_handle();
   h->device = device;
-  for (auto& sl : h->slots) {
-    if (cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (const char* env = getenv("NRQ_HOST_SLOTS")) {
+    int v = atoi(env);
+    if (v >= 1 && v <= kMaxSlots) h->n_slots = v;
+  }
+  bool ok = cudaStreamCreateWithFlags(&h->h2d, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&h->d2h, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < h->n_slots; ++i) {
+    nrq_slot& sl = h->slots[i];
+    if (!ok || cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.up_done, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming) != cudaSuccess) {
       nrq_destroy(h);
       fail("nrq_create: stream / event creation failed");
@@ -374,9 +390,11 @@ void nrq_destroy(nrq_handle* h) {
   for (auto& sl : h->slots) {
     for (auto& s : sl.dev) if (s.first) cudaFree(s.first);
     if (sl.off_stage) cudaFreeHost(sl.off_stage);
-    if (sl.done) cudaEventDestroy(sl.done);
+    for (cudaEvent_t e : {sl.up_done, sl.k_done, sl.done}) if (e) cudaEventDestroy(e);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
+  if (h->h2d) cudaStreamDestroy(h->h2d);
+  if (h->d2h) cudaStreamDestroy(h->d2h);
   delete h;
 }
 
@@ -392,7 +410,8 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
   cudaError_t err = cudaSuccess;
   int rc = 0;
 
-  int64_t kChunkBytes = kChunkBytesDefault;
+  int64_t kChunkBytes = (2 * b->raw_off[R] + 4 * b->starts_off[R] + 2 * b->align_off[R] + 7) / 8;
+  kChunkBytes = kChunkBytes < kChunkBytesMin ? kChunkBytesMin : kChunkBytes > kChunkBytesMax ? kChunkBytesMax : kChunkBytes;
   if (const char* env = getenv("NRQ_HOST_CHUNK_BYTES")) {
     long long v = atoll(env);
     if (v > 0) kChunkBytes = v;
@@ -407,9 +426,9 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     };
     while (hi < R && (hi == lo || in_bytes(lo, hi + 1) <= kChunkBytes)) ++hi;
     const int n = hi - lo;
-    nrq_slot& sl = h->slots[chunk_index % kSlots];
+    nrq_slot& sl = h->slots[chunk_index % h->n_slots];
     cudaStream_t s = sl.stream;
-    // the slot's pinned offset staging is rewritten below: wait for its previous chunk to finish
+    // the slot's buffers and pinned offset staging are reused below: wait for its previous chunk's download
     ce = cudaEventSynchronize(sl.done);
     if (ce != cudaSuccess) { err = ce; break; }
     const size_t need = 3 * (size_t)(n + 1);
@@ -436,7 +455,7 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     auto up = [&](const void* src, size_t bytes) -> void* {
       void* d = dev_buf(sl, k++, bytes ? bytes : 1, &err);
       if (d && bytes && src) {
-        cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, s);
+        cudaError_t e = cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, h->h2d);
         if (e != cudaSuccess) err = e;
       }
       return d;
@@ -472,11 +491,15 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     int64_t ws_bytes = carve(nullptr, n, n_align, p, n_align + n + 64).bytes + 2048;
     void* ws = up(nullptr, (size_t)ws_bytes);
     if (err != cudaSuccess) break;
+    cudaEventRecord(sl.up_done, h->h2d);
+    cudaStreamWaitEvent(s, sl.up_done, 0);
     rc = nrq_resquiggle_batch(&d, p, &o, ws, ws_bytes, s);
     if (rc) break;
+    cudaEventRecord(sl.k_done, s);
+    cudaStreamWaitEvent(h->d2h, sl.k_done, 0);
     auto down = [&](void* dst, const void* src, size_t bytes) {
       if (dst && bytes) {
-        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s);
+        cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->d2h);
         if (e != cudaSuccess) err = e;
       }
     };
@@ -492,11 +515,11 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     down(at(out->ev_length, al0), o.ev_length, 4 * (size_t)n_align);
     down(at(out->ev_base, al0), o.ev_base, (size_t)n_align);
     down(at(out->region_samples, lo), o.region_samples, 4 * (size_t)n);
-    cudaEventRecord(sl.done, s);
+    cudaEventRecord(sl.done, h->d2h);
     lo = hi;
   }
-  for (auto& sl : h->slots) {
-    cudaError_t e = cudaStreamSynchronize(sl.stream);
+  for (int i = -2; i < h->n_slots; ++i) {
+    cudaError_t e = cudaStreamSynchronize(i == -2 ? h->h2d : i == -1 ? h->d2h : h->slots[i].stream);
     if (e != cudaSuccess && err == cudaSuccess) err = e;
   }
   if (rc) return rc;
