@@ -289,7 +289,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   __shared__ __align__(16) unsigned locc[kEvWarps][2][32][4];  // ... and of the packed clip counters
   if (threadIdx.x < 64) rcp_tab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
   __syncthreads();
-  const int warp = threadIdx.x >> 5;
+  // broadcast from lane 0: tells the compiler that the warp index and everything loaded through it are
+  // warp-uniform, so the shuffles and votes below need no convergence barriers around them
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const int r = blockIdx.x * kEvWarps + warp;
   if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
   const int lane = (int)lane_id();

@@ -30,7 +30,8 @@ __device__ __forceinline__ ColMasks load_cols(const uint8_t* __restrict__ ra,
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_align_count(nrq_batch b, int32_t* __restrict__ status, int32_t* __restrict__ n_indels,
               int32_t* __restrict__ n_bases) {
-  int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  // lane-0 broadcast: marks r (and what is loaded through it) warp-uniform for the compiler
+  int r = blockIdx.x * kWarpsPerCta + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (r >= b.n_reads) return;
   int64_t a0 = b.align_off[r];
   int n = (int)(b.align_off[r + 1] - a0);
@@ -97,7 +98,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __restrict__ indel_off,
              int4* __restrict__ indels, int64_t indel_capacity, uint8_t* __restrict__ ev_base,
              int32_t* __restrict__ status_out) {
-  int r = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  // lane-0 broadcast: marks r (and what is loaded through it) warp-uniform for the compiler
+  int r = blockIdx.x * kWarpsPerCta + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
   const unsigned lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;

@@ -49,31 +49,33 @@ struct SegCtx {
 
 // extend_group, resquiggle.py:203-216
 __device__ __forceinline__ int extend_group(const SegCtx& c, int lo, int hi, int maxend,
-                                            int& start, int& stop, int& K) {
+                                            int& start, int& stop, int& K, int& t_start, int& t_stop) {
   int4 a = c.ind[lo], z = c.ind[hi];
   start = a.x;
   stop = maxend;
   if (start < 0 || stop > c.last) return NRQ_ST_BAD_ALIGNMENT;
   K = (z.w + z.z - a.w) + stop - start - 1;
-  while (c.t[stop] - c.t[start] < (K + 2) * c.m) {
+  for (;;) {
+    t_start = c.t[start];
+    t_stop = c.t[stop];
+    if (t_stop - t_start >= (K + 2) * c.m) return NRQ_ST_OK;
     if (start == 0 && stop == c.last) return NRQ_ST_UNSATISFIABLE;
     K += (start > 0) + (stop < c.last);
     start = max(0, start - 1);
     stop = min(c.last, stop + 1);
   }
-  return NRQ_ST_OK;
 }
 
 // the merge loop shared by extend_and_join (:220-225) and extend_for_cpts (:267-272)
 __device__ __forceinline__ int swallow_previous(SegCtx& c, int& lo, int hi, int& maxend,
-                                                int& start, int& stop, int& K) {
+                                                int& start, int& stop, int& K, int& t_start, int& t_stop) {
   while (c.ng > 0) {
     int4 prev = c.groups[c.ng - 1];
     if (start > prev.y) break;
     --c.ng;
     lo = prev.z;
     maxend = max(maxend, prev.w);
-    int st = extend_group(c, lo, hi, maxend, start, stop, K);
+    int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
     if (st != NRQ_ST_OK) return st;
   }
   return NRQ_ST_OK;
@@ -127,14 +129,10 @@ __device__ __forceinline__ int select_cpts_regs(const SegCtx& c, const double* c
     unsigned mi = warp_argmax(best, bi);
     if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
     const int p = (int)mi - 1;
+    if (bi == p) picked |= 1u << (bi >> 5);  // only the owning lane's candidate can be p
 #pragma unroll
-    for (int e = 0; e < E; ++e) {  // blacklist p-m+1 .. p+m (:249-250)
-      int i = lane + 32 * e;
-      if ((unsigned)(i - (p - m + 1)) < (unsigned)(2 * m)) {
-        key[e] = 0ull;
-        if (i == p) picked |= 1u << e;
-      }
-    }
+    for (int e = 0; e < E; ++e)  // blacklist p-m+1 .. p+m (:249-250)
+      if ((unsigned)(lane + 32 * e - (p - m + 1)) < (unsigned)(2 * m)) key[e] = 0ull;
   }
   // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
   int cnt = 0;
@@ -192,12 +190,11 @@ __device__ int select_cpts_mem(const SegCtx& c, double* cs, int nrd, int K, int 
 
 // get_cpts, resquiggle.py:227-255.  1: change-points written to out[outpos..outpos+K); 0: None;
 // < 0: -status.
-__device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, int K, int outpos) {
+__device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int K, int outpos) {
   if (c.limit >= 0 && K > c.limit) return -NRQ_ST_CPTS_LIMIT;
   const unsigned lane = lane_id();
   const int m = c.m;
-  const int t0 = c.t[start];
-  const int n = c.t[stop] - t0;
+  const int n = t_stop - t0;
   const int nrd = n - 2 * m + 1;  // len(running_diffs)
   if (nrd <= 0) return 0;
   const int16_t* s = c.sig + t0;
@@ -258,20 +255,22 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int start, int stop, in
 
 // extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
 __device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
-  int K;
-  int st = extend_group(c, lo, hi, maxend, start, stop, K);
+  int K, t_start, t_stop;  // t[start], t[stop] of the current (start, stop)
+  int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
   if (st != NRQ_ST_OK) return st;
-  st = swallow_previous(c, lo, hi, maxend, start, stop, K);
+  st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
   if (st != NRQ_ST_OK) return st;
   for (;;) {
-    int res = get_cpts(c, start, stop, K, start + c.ind[lo].w + 1);
+    int res = get_cpts(c, t_start, t_stop, K, start + c.ind[lo].w + 1);
     if (res > 0) return NRQ_ST_OK;
     if (res < 0) return -res;
     if (start == 0 && stop == c.last) return NRQ_ST_UNSATISFIABLE;
     K += (start > 0) + (stop < c.last);
     start = max(0, start - 1);
     stop = min(c.last, stop + 1);
-    st = swallow_previous(c, lo, hi, maxend, start, stop, K);
+    t_start = c.t[start];
+    t_stop = c.t[stop];
+    st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
     if (st != NRQ_ST_OK) return st;
   }
 }
