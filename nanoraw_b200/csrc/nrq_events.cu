@@ -276,7 +276,7 @@ __device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_s
 }
 
 #ifndef NRQ_EV_MINB
-#define NRQ_EV_MINB 4
+#define NRQ_EV_MINB 6
 #endif
 __global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
