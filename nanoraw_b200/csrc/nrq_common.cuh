@@ -30,7 +30,11 @@ __device__ __forceinline__ double norm_value(int raw, const NormCoef& c) {
   return x;
 }
 
-__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lane_id() {
+  unsigned l;
+  asm("mov.u32 %0, %%laneid;" : "=r"(l));  // one S2R where the compiler re-derives it, instead of tid & 31
+  return l;
+}
 
 // per-read geometry shared by every kernel
 struct ReadGeom {
