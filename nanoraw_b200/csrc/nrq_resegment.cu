@@ -422,6 +422,10 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.groups = group_scratch + indel_off[r];
     c.ng = 0;
     c.out = new_segs + b.align_off[r] + r;
+    // the two pointers the state machine dereferences most are pinned in vector registers; as warp-uniform
+    // values the compiler otherwise re-forms their addresses on the uniform datapath at every use (4 instructions)
+    asm volatile("" : "+l"(c.t));
+    asm volatile("" : "+l"(c.ind));
     c.m = p.min_seg_len;
     c.limit = p.num_cpts_limit;
     c.buf_sm = my.region;
