@@ -146,13 +146,20 @@ int nrq_find_indels(const nrq_batch* b, int32_t* status, int32_t* n_indels, int3
   if (b->n_reads == 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   int grid = (b->n_reads + nrq::kWarpsPerCta - 1) / nrq::kWarpsPerCta;
-  nrq::k_align_count<<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(*b, status, n_indels, n_bases);
+  // 128-bit row loads need both row buffers on 16-byte boundaries (any cudaMalloc'ed buffer is); otherwise bytes
+  const bool wide = (((uintptr_t)b->read_align | (uintptr_t)b->genome_align) & 15u) == 0;
+  if (wide) nrq::k_align_count<true><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(*b, status, n_indels, n_bases);
+  else nrq::k_align_count<false><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(*b, status, n_indels, n_bases);
   NRQ_CHECK_LAUNCH("k_align_count");
   nrq::k_scan_counts<<<1, 1024, 0, s>>>(n_indels, b->n_reads, indel_off);
   NRQ_CHECK_LAUNCH("k_scan_counts");
   if (indels) {
-    nrq::k_align_fill<<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(
-        *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base, status);
+    if (wide)
+      nrq::k_align_fill<true><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(
+          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base, status);
+    else
+      nrq::k_align_fill<false><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(
+          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base, status);
     NRQ_CHECK_LAUNCH("k_align_fill");
   }
   return 0;

@@ -1,9 +1,14 @@
 // K0 -- get_all_indels (nanoraw/resquiggle.py:142-201) for a batch of reads.
 //
-// One warp per read walks the two alignment rows 32 columns at a time; gap runs are found
-// with ballots, read-base coordinates with popcount prefix sums.  Two launches: a counting
-// pass (also yields Bg/Br and validates the alignment) and, after an exclusive scan of the
-// counts, a fill pass that writes one (start, end, diff, diff_prefix) int4 per indel.
+// One warp per read walks the two alignment rows.  Two launches: a counting pass (also yields Bg/Br and
+// validates the alignment) and, after an exclusive scan of the counts, a fill pass that writes one
+// (start, end, diff, diff_prefix) int4 per indel.
+//
+// Wide path (both row buffers 16-byte aligned, the normal case): 512 columns per step, each lane takes 16
+// consecutive columns with one 128-bit load per row, turns them into 16-bit gap masks with byte-parallel
+// integer arithmetic, finds run starts / ends with shifts on those masks, and gets its run, read-base and
+// genome-base offsets from one packed warp scan.  Byte path (any alignment): 32 columns per step, one byte per
+// lane, masks from ballots.
 #include "nrq_common.cuh"
 
 namespace nrq {
@@ -27,6 +32,55 @@ __device__ __forceinline__ ColMasks load_cols(const uint8_t* __restrict__ ra,
   return m;
 }
 
+
+// ---------------------------------------------------------------- wide path helpers
+// bit k = byte k of w is the gap character (exact for every byte value)
+__device__ __forceinline__ unsigned gap_bits4(unsigned w) {
+  const unsigned t = w ^ (0x01010101u * (unsigned)NRQ_GAP);
+  unsigned y = (t & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+  y = ~(y | t | 0x7f7f7f7fu);               // 0x80 in every zero byte of t
+  return ((y >> 7) * 0x01020408u) >> 24;    // gathers bits 0, 8, 16, 24 into bits 24..27
+}
+
+__device__ __forceinline__ unsigned gap_bits16(const uint4& q) {
+  return gap_bits4(q.x) | (gap_bits4(q.y) << 4) | (gap_bits4(q.z) << 8) | (gap_bits4(q.w) << 12);
+}
+
+// 16 bytes at p (16-byte aligned); bytes outside [lo, hi) are never touched
+__device__ __forceinline__ uint4 load16(const uint8_t* p, const uint8_t* lo, const uint8_t* hi) {
+  if (p >= lo && p + 16 <= hi) return __ldg(reinterpret_cast<const uint4*>(p));
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  for (int j = 0; j < 16; ++j)
+    if (p + j >= lo && p + j < hi) w[j >> 2] |= (unsigned)p[j] << (8 * (j & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+struct Cols16 {
+  unsigned mr, mg, valid;  // 16-bit masks: bit i = column v0 + i - mis is a read gap / genome gap / exists
+  uint4 g;                 // the genome row bytes
+};
+
+// lane's 16 columns of the step starting at virtual column vb (virtual column v = column + mis, so that
+// v % 16 == 0 falls on a 16-byte boundary of both rows)
+__device__ __forceinline__ Cols16 load_cols16(const uint8_t* ra, const uint8_t* ga, const uint8_t* ra_lo,
+                                              const uint8_t* ra_hi, const uint8_t* ga_lo, const uint8_t* ga_hi,
+                                              int mis, int n, int vb) {
+  const int v0 = vb + 16 * (int)lane_id();
+  Cols16 c;
+  const int first = max(mis - v0, 0), last = min(n + mis - v0, 16);  // valid bits [first, last)
+  c.valid = last > first ? (((1u << last) - 1u) & ~((1u << first) - 1u)) : 0u;
+  c.mr = c.mg = 0u;
+  c.g = make_uint4(0u, 0u, 0u, 0u);
+  if (c.valid) {
+    const uint4 r = load16(ra - mis + v0, ra_lo, ra_hi);
+    c.g = load16(ga - mis + v0, ga_lo, ga_hi);
+    c.mr = gap_bits16(r) & c.valid;
+    c.mg = gap_bits16(c.g) & c.valid;
+  }
+  return c;
+}
+
+template <bool WIDE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_align_count(nrq_batch b, int32_t* __restrict__ status, int32_t* __restrict__ n_indels,
               int32_t* __restrict__ n_bases) {
@@ -39,6 +93,34 @@ k_align_count(nrq_batch b, int32_t* __restrict__ status, int32_t* __restrict__ n
   const uint8_t* ga = b.genome_align + a0;
   unsigned carry_r = 0, carry_g = 0;
   int runs = 0, gbases = 0, rbases = 0, bad = 0;
+  if (WIDE) {
+    const int64_t total = b.align_off[b.n_reads];
+    const int mis = (int)(a0 & 15);
+    const int lane = (int)lane_id();
+    unsigned carry = 0;  // bit 0 / 1: the column before this step is a read / genome gap
+    for (int vb = 0; vb < n + mis; vb += 512) {
+      const Cols16 c = load_cols16(ra, ga, b.read_align, b.read_align + total, b.genome_align,
+                                   b.genome_align + total, mis, n, vb);
+      const unsigned tail = (c.mr >> 15) | ((c.mg >> 15) << 1);
+      unsigned before = __shfl_up_sync(0xffffffffu, tail, 1);
+      if (lane == 0) before = carry;
+      carry = __shfl_sync(0xffffffffu, tail, 31);
+      const unsigned sr = c.mr & ~((c.mr << 1) | (before & 1u));
+      const unsigned sg = c.mg & ~((c.mg << 1) | (before >> 1));
+      runs += __popc(sr & 0xffffu) + __popc(sg & 0xffffu);
+      gbases += __popc(~c.mg & c.valid);
+      rbases += __popc(~c.mr & c.valid);
+      bad |= (c.mr & c.mg) != 0u;
+      const int v0 = vb + 16 * lane;
+      const unsigned any = c.mr | c.mg;
+      if ((unsigned)(mis - v0) < 16u) bad |= (any >> (mis - v0)) & 1u;                  // must start on a match column
+      if ((unsigned)(n - 1 + mis - v0) < 16u) bad |= (any >> (n - 1 + mis - v0)) & 1u;  // and end on one
+    }
+    runs = __reduce_add_sync(0xffffffffu, runs);
+    gbases = __reduce_add_sync(0xffffffffu, gbases);
+    rbases = __reduce_add_sync(0xffffffffu, rbases);
+    bad = __any_sync(0xffffffffu, bad);
+  } else
   for (int base = 0; base < n; base += 32) {
     ColMasks m = load_cols(ra, ga, base, n);
     unsigned sr = m.mr & ~((m.mr << 1) | carry_r);
@@ -94,6 +176,7 @@ __device__ __forceinline__ int pymod(int a, int n) {
   return m < 0 ? m + n : m;
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __restrict__ indel_off,
              int4* __restrict__ indels, int64_t indel_capacity, uint8_t* __restrict__ ev_base,
@@ -118,6 +201,58 @@ k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __r
   // pass 1: (run start column, run end column, read bases before the run, gap-in-read?)
   unsigned carry_r = 0, carry_g = 0;
   int idx_base = 0, rbase = 0, gbase = 0;
+  if (WIDE) {
+    const int64_t total = b.align_off[b.n_reads];
+    const int mis = (int)(a0 & 15);
+    unsigned carry = 0;
+    for (int vb = 0; vb < n + mis; vb += 512) {
+      const Cols16 c = load_cols16(ra, ga, b.read_align, b.read_align + total, b.genome_align,
+                                   b.genome_align + total, mis, n, vb);
+      const unsigned tail = (c.mr >> 15) | ((c.mg >> 15) << 1);
+      unsigned before = __shfl_up_sync(0xffffffffu, tail, 1);
+      if (lane == 0) before = carry;
+      carry = __shfl_sync(0xffffffffu, tail, 31);
+      const unsigned prev_r = ((c.mr << 1) | (before & 1u)) & 0xffffu, prev_g = ((c.mg << 1) | (before >> 1)) & 0xffffu;
+      const unsigned sr = c.mr & ~prev_r, sg = c.mg & ~prev_g;
+      const unsigned sany = sr | sg;
+      const unsigned eany = ((~c.mr & prev_r) | (~c.mg & prev_g)) & c.valid;
+      const unsigned rmask = ~c.mr & c.valid, gmask = ~c.mg & c.valid;
+      // one scan for three lane offsets: runs, read bases, genome bases (each at most 512 per step)
+      const unsigned mine = (unsigned)__popc(sany) | ((unsigned)__popc(rmask) << 10) | ((unsigned)__popc(gmask) << 20);
+      unsigned inc = mine;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((int)lane >= o) inc += v;
+      }
+      const unsigned tot = __shfl_sync(0xffffffffu, inc, 31);
+      const unsigned ex = inc - mine;
+      const int run0 = idx_base + (int)(ex & 1023u), r0 = rbase + (int)((ex >> 10) & 1023u);
+      const int col0 = vb + 16 * (int)lane - mis;
+      int k = 0;
+      for (unsigned todo = sany; todo; todo &= todo - 1u, ++k) {
+        const int i = __ffs(todo) - 1;
+        int4* o = out + run0 + k;
+        o->x = col0 + i;
+        o->z = r0 + __popc(rmask & ((1u << i) - 1u));
+        o->w = (int)((sr >> i) & 1u);
+      }
+      for (unsigned todo = eany; todo; todo &= todo - 1u) {
+        const int i = __ffs(todo) - 1;
+        out[run0 + __popc(sany & ((1u << i) - 1u)) - 1].y = col0 + i;
+      }
+      if (bases) {
+        uint8_t* dst = bases + gbase + (int)(ex >> 20);
+        const unsigned w[4] = {c.g.x, c.g.y, c.g.z, c.g.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if ((gmask >> i) & 1u) *dst++ = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+      }
+      idx_base += (int)(tot & 1023u);
+      rbase += (int)((tot >> 10) & 1023u);
+      gbase += (int)(tot >> 20);
+    }
+  } else
   for (int base = 0; base < n; base += 32) {
     ColMasks m = load_cols(ra, ga, base, n);
     if (bases) {

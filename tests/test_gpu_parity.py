@@ -125,6 +125,43 @@ def test_golden_indels(engine):
         assert np.array_equal(bases[a0:a0 + n_bases[r]], g[g != ord('-')])
 
 
+def test_indel_scan_byte_path_equals_wide_path(engine):
+    """nrq_find_indels takes 128-bit row loads when both alignment buffers sit on 16-byte boundaries and falls
+    back to byte loads otherwise: same indels, bases and statuses either way (golden + seeded + malformed reads)"""
+    import copy
+    import torch
+    from nanoraw_b200.engine import DeviceBatch
+    reads = [c.read for c in CASES if 'indels' in c.a]
+    reads += synth.make_reads(24, synth.SynthConfig(span_mean=700, span_sd=300, seed_base=61000),
+                              genome=synth.make_genome(80_000, seed=3))
+    reads += synth.make_reads(6, synth.config_indel_dense(seed_base=62000), genome=synth.make_genome(80_000, seed=4))
+    bad = copy.copy(reads[3])
+    bad.read_align = bad.read_align[:-1] + b'-'          # ends on a gap column
+    reads.append(bad)
+    db = engine.upload(ReadBatch.from_reads(reads))
+    assert db.t['read_align'].data_ptr() % 16 == 0 and db.t['genome_align'].data_ptr() % 16 == 0
+    wide = engine.find_indels(db)
+    for shift in (1, 7, 8):
+        t = dict(db.t)
+        for name in ('read_align', 'genome_align'):
+            buf = torch.zeros(db.t[name].numel() + 32, dtype=torch.uint8, device=db.t[name].device)
+            buf[shift:shift + db.t[name].numel()] = db.t[name]
+            t[name] = buf[shift:shift + db.t[name].numel()]
+            assert t[name].data_ptr() % 16 == shift
+        narrow = engine.find_indels(DeviceBatch.from_tensors(t, db.n_reads, db.total_align, db.device, host=db.host))
+        for a, b in zip(wide, narrow):
+            assert np.array_equal(a, b)
+    status, n_ind, n_bases, off, indels, bases = wide
+    assert status[-1] != 0 and (status[:-1] == 0).all()
+    for r, rd in enumerate(reads[:-1]):
+        want = np.array([tuple(i) for i in orc.get_all_indels(rd.read_align.decode(), rd.genome_align.decode())],
+                        dtype=np.int64).reshape(-1, 3)
+        assert np.array_equal(indels[off[r]:off[r + 1], :3], want), r
+        g = np.frombuffer(rd.genome_align, dtype=np.uint8)
+        a0 = int(db.host.align_off[r])
+        assert np.array_equal(bases[a0:a0 + n_bases[r]], g[g != ord('-')]), r
+
+
 def test_golden_normalised_signal(engine):
     from nanoraw_b200.engine import ResquiggleParams
     for key, cases in groups_by_params().items():
