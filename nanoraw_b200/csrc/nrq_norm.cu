@@ -138,7 +138,9 @@ __device__ __forceinline__ unsigned long long dbits(double x) {
 // ---------------------------------------------------------------- K1
 __global__ void __launch_bounds__(kNormThreads, NRQ_NORM_MINB)
 k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __restrict__ sv_out) {
-  __shared__ unsigned hist[kWin];
+  // hist[-1] counts the samples below the window, hist[kWin] those above it
+  __shared__ unsigned hist_all[kWin + 2];
+  unsigned* const hist = hist_all + 1;
   __shared__ long long sh_red[kNormThreads / 32];
   __shared__ unsigned sh_scan[kNormThreads / 32];
   __shared__ int sh_res[2];
@@ -173,22 +175,24 @@ k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __
   long long below = 0, above = 0;
   bool win_ok = false;
   if (need_hist && !force_general) {
-    for (int i = tid; i < kWin; i += kNormThreads) hist[i] = 0;
+    for (int i = tid; i < kWin + 2; i += kNormThreads) hist_all[i] = 0;
     {  // pivot: median of three samples, so that a single spike cannot misplace the window
       int a = sig[n / 4], c = sig[n / 2], e = sig[(3 * (long long)n) / 4];
       int piv = max(min(a, c), min(max(a, c), e));
       lo_w = piv - kWin / 2;
     }
     __syncthreads();
-    int nb = 0, na = 0;
+    // one clamped, branch-free shared-memory increment per sample; the table's shared address is formed once
+    // (left to the compiler it is re-derived per sample, and the two-sided test costs four branch instructions)
+    unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist_all);
+    asm volatile("" : "+r"(hist_sa));
     for_each_sample(sig, n, [&](int v) {
-      int idx = v - lo_w;
-      if ((unsigned)idx < (unsigned)kWin) atomicAdd(&hist[idx], 1u);
-      else if (idx < 0) ++nb;
-      else ++na;
+      const int slot = min(max(v - lo_w, -1), kWin) + 1;
+      asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * (unsigned)slot) : "memory");
     });
-    below = block_sum(nb, sh_red);
-    above = block_sum(na, sh_red);
+    __syncthreads();
+    below = hist[-1];
+    above = hist[kWin];
     win_ok = (below <= k1) && (k2 < n - above);
   }
 
