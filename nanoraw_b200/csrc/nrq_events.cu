@@ -192,8 +192,12 @@ __device__ __forceinline__ double ev_rcp(double y) {
 }
 
 __device__ __forceinline__ double ev_sqrt(double y) {
-  if (!(y > 1e-30 && y < 1e30)) return sqrt(y);
-  double r = (double)rsqrtf((float)y);
+  // 2^-100 <= y < 2^100 (one integer compare on the exponent word; zero, NaN and negatives fall out too):
+  // the float seed needs no denormal handling
+  if ((unsigned)(__double2hiint(y) - 0x39b00000) >= (unsigned)(0x46300000 - 0x39b00000)) return sqrt(y);
+  float seed;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(seed) : "f"((float)y));
+  double r = (double)seed;
   const double h = 0.5 * y;
   r = r * fma(-h * r, r, 1.5);
   r = r * fma(-h * r, r, 1.5);
@@ -272,20 +276,51 @@ __device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_s
   }
   long long mid = ((long long)max(k.u_lo, -32768) + (long long)min(k.u_hi, 32767)) / 2;
   k.pivot = coef.clip ? (int)mid : pivot_sample;
+  // a short unclipped range is summed as d = code - u_lo >= 0: no select per sample, 32-bit sums per step
+  if (coef.clip && k.u_hi >= k.u_lo && k.u_hi - k.u_lo <= 2047) k.pivot = k.u_lo;
   return k;
 }
 
 #ifndef NRQ_EV_MINB
 #define NRQ_EV_MINB 6
 #endif
+
+// one step of the inclusive warp scan of (a, b): the shuffle's own predicate says whether lane - o exists, so
+// no lane compare is needed
+__device__ __forceinline__ void ev_scan_step(int& a, unsigned& b, int o) {
+  asm volatile(
+      "{ .reg .pred p; .reg .b32 t0, t1;\n"
+      "shfl.sync.up.b32 t0|p, %0, %2, 0, 0xffffffff;\n"
+      "shfl.sync.up.b32 t1, %1, %2, 0, 0xffffffff;\n"
+      "@p add.s32 %0, %0, t0;\n"
+      "@p add.u32 %1, %1, t1; }"
+      : "+r"(a), "+r"(b) : "r"(o));
+}
+
+// lane-local exclusive prefixes (sum d, sum d^2) of one step: lane t's eight pairs, padded to 80 bytes so that
+// the four 128-bit stores of a warp are bank-conflict free
+struct __align__(16) EvLoc {
+  int2 p[8];
+  int2 pad[2];
+};
+
+__device__ __forceinline__ int2 ev_loc_at(const EvLoc* locw, int sl) {  // pair of slot sl = 8 t + j
+  return *reinterpret_cast<const int2*>(reinterpret_cast<const char*>(locw) + sl * 8 + (sl >> 3) * 16);
+}
+
+#ifndef NRQ_EV_AHEAD
+#define NRQ_EV_AHEAD 2
+#endif
+constexpr int kEvAhead = NRQ_EV_AHEAD;  // steps between a prefetch and the load it serves
+constexpr int kNoPos = 0x3fffffff;  // "no such boundary": never inside a step
+
 __global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
               const int32_t* __restrict__ new_segs, const int32_t* __restrict__ status,
               double* __restrict__ norm_mean, double* __restrict__ norm_stdev,
               uint32_t* __restrict__ ev_start, uint32_t* __restrict__ ev_length) {
   __shared__ double rcp_tab[64];
-  __shared__ __align__(16) int loc1[kEvWarps][2][32][4];       // lane-local exclusive prefixes of d
-  __shared__ __align__(16) unsigned loc2[kEvWarps][2][32][4];  // ... and of d^2
+  __shared__ EvLoc loc[kEvWarps][32];                          // lane-local exclusive prefixes of (d, d^2)
   __shared__ __align__(16) unsigned locc[kEvWarps][2][32][4];  // ... and of the packed clip counters
   if (threadIdx.x < 64) rcp_tab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
   __syncthreads();
@@ -301,6 +336,11 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   const int32_t* segs = new_segs + b.align_off[r] + r;
   const size_t off = (size_t)b.align_off[r];
   const int n_norm = g.n_norm;
+  EvLoc* const locw = loc[warp];
+  double* const o_mean = norm_mean + off;
+  double* const o_sd = norm_stdev + off;
+  uint32_t* const o_start = ev_start + off;
+  uint32_t* const o_length = ev_length + off;
 
   const EvClass k = ev_classify(coef, (int)g.sig[n_norm / 2]);  // every lane: a handful of divisions
   const int u_lo = k.u_lo, u_hi = k.u_hi, pivot = k.pivot;
@@ -315,6 +355,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   // d^2 summed over one 256-sample step fits 32 bits when |d| <= 2048
   const unsigned range = (unsigned)(u_hi - u_lo);
   const bool narrow = coef.clip && u_hi >= u_lo && range <= 4094u;
+  const bool tiny = narrow && pivot == u_lo;  // ev_classify: unclipped range <= 2047 codes, d = code - u_lo >= 0
   const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 
   // steps are laid out on 16-byte boundaries of the raw buffer: sample i sits at slot i + a
@@ -325,53 +366,86 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   long long run1 = 0, prev1 = 0;
   unsigned long long run2 = 0, prev2 = 0;
   int runl = 0, runh = 0, prevl = 0, prevh = 0;
-  int cur = 0;  // next boundary to resolve (0 .. nb)
+  int cur = 0;      // next boundary to resolve (0 .. nb)
+  int prevpos = 0;  // position of boundary cur - 1
+  // position of boundary cur + lane: np.split(norm_signal, new_segs[1:-1]) -- the first piece starts at 0, the
+  // last runs to the end (:64).  Loaded as soon as cur is known, a step ahead of its use.
+  auto load_pos = [&](int c) {
+    const int bidx = c + lane;
+    int q = kNoPos;
+    if (bidx <= nb) q = (bidx == 0) ? 0 : (bidx == nb ? n_norm : __ldg(segs + bidx));
+    return q;
+  };
+  int pos = load_pos(0);
+  auto interior = [&](int t0) { return narrow && t0 >= a && t0 + kSub - a <= n_norm; };
 
   for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
     const int slot = tile0 + 8 * lane;
     // ================= fast step: interior step of a read with a narrow unclipped range =================
-    if (narrow && tile0 >= a && tile0 + kSub - a <= n_norm) {
+    if (interior(tile0)) {
       const int4 q = __ldg(reinterpret_cast<const int4*>(base_al + slot));
+      // the samples two steps ahead start their trip from HBM now (no register held for them)
+      if (slot + kEvAhead * kSub + 8 <= n_norm)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base_al + slot + kEvAhead * kSub));
       int l1[8];
       unsigned l2[8];
       int s1 = 0;
-      unsigned s2 = 0, out_of_range = 0;
+      unsigned s2 = 0, cnt = 0;
+      bool anyc = true;
+      if (tiny) {  // optimistic: no clipped sample in the step, d = code - u_lo needs no select
+        bool oor = false;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int v = unpack16(q, j);
-        const bool unc = (unsigned)(v - u_lo) <= range;
-        out_of_range |= unc ? 0u : 1u;
-        const int d = unc ? v - pivot : 0;
-        l1[j] = s1;
-        l2[j] = s2;
-        s1 += d;
-        s2 += (unsigned)(d * d);
+        for (int j = 0; j < 8; ++j) {
+          const unsigned d = (unsigned)(unpack16(q, j) - u_lo);
+          oor |= d > range;
+          l1[j] = s1;
+          l2[j] = s2;
+          s1 += (int)d;
+          s2 += d * d;
+        }
+        anyc = __any_sync(0xffffffffu, oor);
       }
-      *reinterpret_cast<int4*>(loc1[warp][0][lane]) = make_int4(l1[0], l1[1], l1[2], l1[3]);
-      *reinterpret_cast<int4*>(loc1[warp][1][lane]) = make_int4(l1[4], l1[5], l1[6], l1[7]);
-      *reinterpret_cast<uint4*>(loc2[warp][0][lane]) = make_uint4(l2[0], l2[1], l2[2], l2[3]);
-      *reinterpret_cast<uint4*>(loc2[warp][1][lane]) = make_uint4(l2[4], l2[5], l2[6], l2[7]);
-      // clipped samples are rare: only steps that contain one carry the (below, above) counters
-      const bool anyc = __any_sync(0xffffffffu, out_of_range);
-      unsigned cnt = 0;
       if (anyc) {
-        unsigned lc[8];
+        unsigned out_of_range = 0;
+        s1 = 0;
+        s2 = 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int v = unpack16(q, j);
-          lc[j] = cnt;
-          cnt += (v < u_lo ? 1u : 0u) + (v > u_hi ? 65536u : 0u);
+          const bool unc = (unsigned)(v - u_lo) <= range;
+          out_of_range |= unc ? 0u : 1u;
+          const int d = unc ? v - pivot : 0;
+          l1[j] = s1;
+          l2[j] = s2;
+          s1 += d;
+          s2 += (unsigned)(d * d);
         }
-        *reinterpret_cast<uint4*>(locc[warp][0][lane]) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
-        *reinterpret_cast<uint4*>(locc[warp][1][lane]) = make_uint4(lc[4], lc[5], lc[6], lc[7]);
+        // clipped samples are rare: only steps that contain one carry the (below, above) counters
+        anyc = __any_sync(0xffffffffu, out_of_range);
+        if (anyc) {
+          unsigned lc[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int v = unpack16(q, j);
+            lc[j] = cnt;
+            cnt += (v < u_lo ? 1u : 0u) + (v > u_hi ? 65536u : 0u);
+          }
+          *reinterpret_cast<uint4*>(locc[warp][0][lane]) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
+          *reinterpret_cast<uint4*>(locc[warp][1][lane]) = make_uint4(lc[4], lc[5], lc[6], lc[7]);
+        }
+      }
+      {
+        int4* dst = reinterpret_cast<int4*>(locw[lane].p);
+        dst[0] = make_int4(l1[0], (int)l2[0], l1[1], (int)l2[1]);
+        dst[1] = make_int4(l1[2], (int)l2[2], l1[3], (int)l2[3]);
+        dst[2] = make_int4(l1[4], (int)l2[4], l1[5], (int)l2[5]);
+        dst[3] = make_int4(l1[6], (int)l2[6], l1[7], (int)l2[7]);
       }
       int i1 = s1;
       unsigned i2 = s2, ic = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        int t1 = __shfl_up_sync(0xffffffffu, i1, o);
-        unsigned t2 = __shfl_up_sync(0xffffffffu, i2, o);
-        if (lane >= o) { i1 += t1; i2 += t2; }
+        ev_scan_step(i1, i2, o);
         if (anyc) {
           unsigned tc = __shfl_up_sync(0xffffffffu, ic, o);
           if (lane >= o) ic += tc;
@@ -385,26 +459,57 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       __syncwarp();
       const int tile_end = tile0 + kSub;
       for (;;) {
-        const int bidx = cur + lane;
-        int pos = 0;
-        bool inb = false;
-        if (bidx <= nb) {
-          pos = (bidx == 0) ? 0 : (bidx == nb ? n_norm : segs[bidx]);
-          inb = pos + a < tile_end;
-        }
+        const bool inb = pos + a < tile_end;
         const unsigned bal = __ballot_sync(0xffffffffu, inb);
         const int cntb = __popc(bal);
         if (cntb == 0) break;
-        const int sl = inb ? pos + a - tile0 : 0;
-        const int t = sl >> 3, jj = sl & 7;
-        const int E1 = __shfl_sync(0xffffffffu, ex1, t) + loc1[warp][jj >> 2][t][jj & 3];
-        const unsigned E2 = __shfl_sync(0xffffffffu, ex2, t) + loc2[warp][jj >> 2][t][jj & 3];
-        const int pE1 = __shfl_up_sync(0xffffffffu, E1, 1);
-        const unsigned pE2 = __shfl_up_sync(0xffffffffu, E2, 1);
-        const int bpos = __shfl_up_sync(0xffffffffu, pos, 1);
+        const int sl = (pos + a - tile0) & (kSub - 1);
+        const int t = sl >> 3;
+        const int2 L = ev_loc_at(locw, sl);
+        const int E1 = __shfl_sync(0xffffffffu, ex1, t) + L.x;
+        const unsigned E2 = __shfl_sync(0xffffffffu, ex2, t) + (unsigned)L.y;
+        int pE1 = __shfl_up_sync(0xffffffffu, E1, 1);
+        unsigned pE2 = __shfl_up_sync(0xffffffffu, E2, 1);
+        int bpos = __shfl_up_sync(0xffffffffu, pos, 1);
+        // sums carried in from earlier steps for the base that ends at the first boundary of this round
+        const long long c1 = run1 - prev1;
+        const unsigned long long c2 = run2 - prev2;
+        // ---- common round: no clipped sample in play, bases 1 .. nb - 2 only, carried sums fit 32 bits
+        if (!anyc && cur >= 2 && cur + 32 < nb && (c2 >> 30) == 0ull && runl == prevl && runh == prevh) {
+          if (lane == 0) { pE1 = -(int)c1; pE2 = 0u - (unsigned)c2; bpos = prevpos; }
+          if (inb) {
+            const int n = pos - bpos;
+            const int S1 = E1 - pE1;        // |S1| <= S2 < 2^32: d is an integer
+            const unsigned S2 = E2 - pE2;
+            const double dn = (double)n;
+            const double rn = (unsigned)n < 64u ? rcp_tab[n] : ev_rcp(dn);
+            const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
+            double mean = sum_u * rn, sd = qnan;
+            if (R.compute_sd) {
+              const unsigned long long num =
+                  (unsigned long long)(unsigned)n * (unsigned long long)S2 - (unsigned long long)((long long)S1 * (long long)S1);
+              sd = ev_sqrt((double)num * rn * R.inv_scale2 * rn);
+            }
+            if (n <= 0) { mean = qnan; sd = qnan; }
+            const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
+            o_mean[o] = mean;
+            o_sd[o] = sd;
+            o_start[o] = (uint32_t)bpos;
+            o_length[o] = (uint32_t)n;
+          }
+          prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
+          prev2 = run2 + __shfl_sync(0xffffffffu, E2, cntb - 1);
+          prevpos = __shfl_sync(0xffffffffu, pos, cntb - 1);
+          cur += cntb;
+          pos = load_pos(cur);
+          if (cntb < 32) break;
+          continue;
+        }
+        // ---- any other round of a fast step
+        const int bidx = cur + lane;
         int el = runl, eh = runh, pl = runl, ph = runh;
         if (anyc) {
-          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][jj >> 2][t][jj & 3];
+          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][(sl & 7) >> 2][t][sl & 3];
           el += (int)(EC & 0xffffu);
           eh += (int)(EC >> 16);
           pl = __shfl_up_sync(0xffffffffu, el, 1);
@@ -421,8 +526,8 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             long long S1;
             unsigned long long S2;
             if (lane == 0) {  // the base may have begun in an earlier step
-              S1 = run1 + E1 - prev1;
-              S2 = run2 + E2 - prev2;
+              S1 = c1 + E1;
+              S2 = c2 + E2;
               pl = prevl;
               ph = prevh;
             } else {
@@ -440,7 +545,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         prev2 = run2 + __shfl_sync(0xffffffffu, E2, cntb - 1);
         prevl = anyc ? __shfl_sync(0xffffffffu, el, cntb - 1) : runl;
         prevh = anyc ? __shfl_sync(0xffffffffu, eh, cntb - 1) : runh;
+        prevpos = __shfl_sync(0xffffffffu, pos, cntb - 1);
         cur += cntb;
+        pos = load_pos(cur);
         if (cntb < 32) break;
       }
       run1 += tot1;
@@ -493,13 +600,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
     const int tile_end = tile0 + kSub;
     for (;;) {
       const int bidx = cur + lane;
-      int pos = 0;
-      bool inb = false;
-      if (bidx <= nb) {
-        // np.split(norm_signal, new_segs[1:-1]): first piece starts at 0, last runs to the end (:64)
-        pos = (bidx == 0) ? 0 : (bidx == nb ? n_norm : segs[bidx]);
-        inb = pos + a < tile_end;
-      }
+      const bool inb = pos + a < tile_end;
       const unsigned bal = __ballot_sync(0xffffffffu, inb);
       const int cntb = __popc(bal);
       if (cntb == 0) break;
@@ -550,7 +651,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       prev2 = __shfl_sync(0xffffffffu, e2, cntb - 1);
       prevl = __shfl_sync(0xffffffffu, el, cntb - 1);
       prevh = __shfl_sync(0xffffffffu, eh, cntb - 1);
+      prevpos = __shfl_sync(0xffffffffu, pos, cntb - 1);
       cur += cntb;
+      pos = load_pos(cur);
       if (cntb < 32) break;
     }
     run1 += tot1;
