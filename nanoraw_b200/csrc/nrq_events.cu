@@ -312,7 +312,8 @@ __device__ __forceinline__ int2 ev_loc_at(const EvLoc* locw, int sl) {  // pair 
 #define NRQ_EV_AHEAD 2
 #endif
 constexpr int kEvAhead = NRQ_EV_AHEAD;  // steps between a prefetch and the load it serves
-constexpr int kNoPos = 0x3fffffff;  // "no such boundary": never inside a step
+constexpr int kNoPos = 0x3fffffff;
+  // "no such boundary": never inside a step
 
 __global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
@@ -370,19 +371,22 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   int prevpos = 0;  // position of boundary cur - 1
   // position of boundary cur + lane: np.split(norm_signal, new_segs[1:-1]) -- the first piece starts at 0, the
   // last runs to the end (:64).  Loaded as soon as cur is known, a step ahead of its use.
-  auto load_pos = [&](int c) {
-    const int bidx = c + lane;
-    int q = kNoPos;
-    if (bidx <= nb) q = (bidx == 0) ? 0 : (bidx == nb ? n_norm : __ldg(segs + bidx));
+  auto load_pos = [&](int c) {  // c > 0 (cur only grows, and boundary 0 is the first one resolved)
+    const unsigned bidx = (unsigned)(c + lane);
+    int q = bidx == (unsigned)nb ? n_norm : kNoPos;
+    if (bidx < (unsigned)nb) q = __ldg(segs + bidx);
     return q;
   };
   int pos = load_pos(0);
-  auto interior = [&](int t0) { return narrow && t0 >= a && t0 + kSub - a <= n_norm; };
+  if (lane == 0) pos = 0;  // boundary 0 sits at sample 0 whatever new_segs[0] says
+  // interior steps (all 256 samples belong to the read) of a read with a narrow unclipped range: [fast_lo, fast_hi)
+  const int fast_lo = narrow ? ((a + kSub - 1) / kSub) * kSub : 0x7fffffff;
+  const int fast_hi = n_norm + a - kSub + 1;
 
   for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
     const int slot = tile0 + 8 * lane;
     // ================= fast step: interior step of a read with a narrow unclipped range =================
-    if (interior(tile0)) {
+    if (tile0 >= fast_lo && tile0 < fast_hi) {
       const int4 q = __ldg(reinterpret_cast<const int4*>(base_al + slot));
       // the samples two steps ahead start their trip from HBM now (no register held for them)
       if (slot + kEvAhead * kSub + 8 <= n_norm)
