@@ -12,6 +12,9 @@ selected backend:
   use it.  It keeps h5py's refusal to store ``None`` attributes (SURVEY.md
   section 8b quirks) so reads that fail in the reference fail here too.
 
+* ``'native'`` -- ``hdf5_min.py``: this repo's own reader / writer for the slice of HDF5 that
+  FAST5 files use (what ``'auto'`` falls back to when h5py is missing), same object model.
+
 The object model is deliberately h5py's so the same caller code runs on both.
 """
 import threading
@@ -22,7 +25,7 @@ _BACKEND = ['auto']
 
 
 def set_backend(name):
-    assert name in ('auto', 'h5py', 'mem')
+    assert name in ('auto', 'h5py', 'mem', 'native')
     _BACKEND[0] = name
 
 
@@ -39,11 +42,20 @@ def _split(path):
 
 
 class MemAttrs(dict):
+    _hook = None  # called on every change (the native backend marks the file dirty)
+
     def __setitem__(self, key, value):
         if value is None:
             # h5py: np.asarray(None) is object dtype, which has no HDF5 type
             raise TypeError("Object dtype dtype('O') has no native HDF5 equivalent")
         dict.__setitem__(self, key, value)
+        if self._hook:
+            self._hook()
+
+    def __delitem__(self, key):
+        dict.__delitem__(self, key)
+        if self._hook:
+            self._hook()
 
 
 class MemDataset(object):
@@ -73,11 +85,60 @@ class MemDataset(object):
         return self._data.dtype
 
 
+class LazyDataset(MemDataset):
+    """dataset whose contents are decoded from the file on first access (native HDF5 backend)"""
+
+    def __init__(self, loader, dtype, shape, compression=None):
+        self._loader = loader
+        self._cache = None
+        self._dtype = dtype
+        self._shape = tuple(shape)
+        self.attrs = MemAttrs()
+        self.compression = compression
+
+    @property
+    def _data(self):
+        if self._cache is None:
+            self._cache = np.asarray(self._loader())
+        return self._cache
+
+    def __len__(self):
+        return self._shape[0]
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+
 class MemGroup(object):
     def __init__(self, writable=True):
         self._children = {}
         self.attrs = MemAttrs()
         self._writable = [writable]
+        self._hook = None
+
+    def _set_hook(self, hook):
+        """`hook()` is called whenever this subtree changes"""
+        self._hook = hook
+        self.attrs._hook = hook
+        for child in self._children.values():
+            if isinstance(child, MemGroup):
+                child._set_hook(hook)
+            else:
+                child.attrs._hook = hook
+
+    def _adopt(self, node):
+        if self._hook:
+            if isinstance(node, MemGroup):
+                node._set_hook(self._hook)
+            else:
+                node.attrs._hook = self._hook
+            self._hook()
+        return node
 
     def _walk(self, path, create=False):
         node = self
@@ -87,7 +148,7 @@ class MemGroup(object):
             if part not in node._children:
                 if not create:
                     raise KeyError("Unable to open object (component not found: %s)" % part)
-                node._children[part] = MemGroup()
+                node._children[part] = node._adopt(MemGroup())
             node = node._children[part]
         return node
 
@@ -105,13 +166,15 @@ class MemGroup(object):
         parts = _split(path)
         parent = self._walk('/'.join(parts[:-1]))
         del parent._children[parts[-1]]
+        if self._hook:
+            self._hook()
 
     def create_group(self, path):
         parts = _split(path)
         parent = self._walk('/'.join(parts[:-1]), create=True)
         if parts[-1] in parent._children:
             raise ValueError('Unable to create group (name already exists)')
-        parent._children[parts[-1]] = MemGroup()
+        parent._children[parts[-1]] = parent._adopt(MemGroup())
         return parent._children[parts[-1]]
 
     def require_group(self, path):
@@ -122,7 +185,7 @@ class MemGroup(object):
         parent = self._walk('/'.join(parts[:-1]), create=True)
         if parts[-1] in parent._children:
             raise ValueError('Unable to create dataset (name already exists)')
-        parent._children[parts[-1]] = MemDataset(data, compression)
+        parent._children[parts[-1]] = parent._adopt(MemDataset(data, compression))
         return parent._children[parts[-1]]
 
     def keys(self):
@@ -205,12 +268,12 @@ def open_fast5(name, mode='r'):
     backend = _BACKEND[0]
     if name.startswith('mem://') or backend == 'mem':
         return MemFile(name, mode)
-    if backend == 'auto' and not _have_h5py():
-        raise ImportError(
-            'h5py is not installed: on-disk FAST5 files cannot be opened. '
-            "Use mem:// names (tests/bench) or install h5py.")
-    import h5py
-    return h5py.File(name, mode)
+    if backend == 'h5py' or (backend == 'auto' and _have_h5py()):
+        import h5py
+        return h5py.File(name, mode)
+    # no h5py / libhdf5 in this environment: the built-in reader / writer (hdf5_min.py)
+    from . import hdf5_min
+    return hdf5_min.NativeFile(name, mode)
 
 
 def read_dataset(ds):

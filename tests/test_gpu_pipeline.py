@@ -18,7 +18,7 @@ FAKE_BWA = os.path.join(HERE, 'tools', 'fake_bwa.py')
 
 
 def make_basecalled_fast5(name, read, events, start_time=0):
-    f = fast5_io.MemFile(name, 'w')
+    f = fast5_io.open_fast5(name, 'w')
     rd = f.create_group('Raw/Reads/Read_3')
     rd.create_dataset('Signal', data=read.raw)
     rd.attrs['read_id'] = read.read_id
@@ -33,8 +33,13 @@ def make_basecalled_fast5(name, read, events, start_time=0):
     f.close()
 
 
-def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch):
+@pytest.mark.parametrize('backend', ['mem', 'native'])
+def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch, backend):
+    """backend 'mem': FAST5 files in the in-process store; 'native': real files on disk, read and rewritten
+    by this repo's own HDF5 reader / writer (hdf5_min.py)"""
     from nanoraw_b200 import frontend
+    monkeypatch.setattr(fast5_io, '_BACKEND', [backend if backend == 'native' else 'auto'])
+    prefix = 'mem://pipeline/' if backend == 'mem' else str(tmp_path) + '/'
     from nanoraw_b200 import resquiggle as rsq
     from oracle import resquiggle_oracle as orc
 
@@ -49,7 +54,7 @@ def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch):
         # the basecaller saw a few extra bases each side that the mapper soft-clips
         clip = (i % 3, (2 * i) % 5)
         events = synth.to_basecall_events(read, stay_rate=0.12, clip_bases=clip, seed=i)
-        name = 'mem://pipeline/read_%02d.fast5' % i
+        name = prefix + 'read_%02d.fast5' % i
         # samples taken by the clipped leading bases (a base starts at every moving event)
         base_events = np.flatnonzero(events['move'] == 1)
         lead = int(np.round(events['start'][base_events[clip[0]]] * 4000.0))
@@ -63,7 +68,7 @@ def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch):
         names.append(name)
         reads.append(read)
     # one file with no alignment, one file without basecalls
-    unaligned = 'mem://pipeline/unaligned.fast5'
+    unaligned = prefix + 'unaligned.fast5'
     extra = synth.make_read(genome, synth.kmer_levels(cfg), cfg, 99)
     make_basecalled_fast5(unaligned, extra, synth.to_basecall_events(extra, seed=99))
     rec_path = tmp_path / 'records.json'
@@ -100,7 +105,7 @@ def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch):
         assert rows[0].encode() == read.read_align and rows[1].encode() == read.genome_align
         assert loc.Strand == read.strand and loc.Start == read.genome_start
         want = orc.resquiggle_read(read.raw, int(read_start), starts, rows[0], rows[1])
-        sub = fast5_io.MemFile(name)['/Analyses/RawGenomeCorrected_000/BaseCalled_template']
+        sub = fast5_io.open_fast5(name, 'r')['/Analyses/RawGenomeCorrected_000/BaseCalled_template']
         ev = sub['Events'][()]
         assert np.array_equal(ev['start'], want['events']['start'])
         assert np.array_equal(ev['length'], want['events']['length'])
