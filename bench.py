@@ -394,6 +394,8 @@ def gpu_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_leg(args, reads)
+        if world == 1 and args.fast5_files > 0:
+            line['e2e_fast5'] = fast5_leg(args, reads)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -476,6 +478,65 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
     return samples, e2e_ms, h2d, d2h
 
 
+def fast5_leg(args, reads):
+    """The re-squiggle worker's whole body (resquiggle.py:403-440 -> 318-401) on FAST5 files on disk: open each
+    file and read its raw signal, one device batch through the C ABI, RawGenomeCorrected written back into each
+    file.  File access is this repo's own HDF5 reader / writer on NRQ_IO_PROCS host processes.  Alignments are
+    the synthetic ones (the mapper stays external), handed over as the queue items the alignment workers make."""
+    import shutil
+    import tempfile
+    from nanoraw_b200 import fast5_io, fast5_jobs
+    from nanoraw_b200 import resquiggle as rsq
+    from nanoraw_b200.frontend import genomeLoc, readInfo
+    n = args.fast5_files
+    tmp = tempfile.mkdtemp(prefix='nrq_fast5_')
+    try:
+        jobs = [(os.path.join(tmp, 'read_%05d.fast5' % i), reads[i % len(reads)]) for i in range(n)]
+        t0 = time.perf_counter()
+        sizes = fast5_jobs.map_jobs(synth.write_basecalled_fast5_job, jobs)
+        setup_s = time.perf_counter() - t0
+
+        def pending_reads():
+            out = []
+            for fn, read in jobs:
+                info = readInfo(os.path.basename(fn), 'BaseCalled_template', 0, 0, 0, 0, 0, 0)
+                loc = genomeLoc(int(read.genome_start), read.strand, read.chrom)
+                out.append(rsq._PendingRead(fn, ((read.read_align, read.genome_align), loc, read.starts,
+                                                 int(read.read_start_rel_to_raw), info)))
+            return out
+
+        def one_pass():
+            pend = pending_reads()
+            failed = []
+            for lo in range(0, len(pend), rsq.DEVICE_BATCH_READS):
+                failed += rsq.resquiggle_reads_batch(
+                    pend[lo:lo + rsq.DEVICE_BATCH_READS], 'median', 5, None, None, 'Basecall_1D_000',
+                    'RawGenomeCorrected_000', True, None)
+            return failed
+
+        one_pass()                                   # warm-up: pool start-up, pinned staging, kernels
+        fast5_jobs.map_jobs(synth.drop_corrected_job, jobs)      # back to the state prep_fast5 leaves (not timed)
+        t0 = time.perf_counter()
+        failed = one_pass()
+        dt = time.perf_counter() - t0
+        samples_of = {fn: read.n_samples for fn, read in jobs}
+        ok_samples = sum(samples_of.values()) - sum(samples_of[pr.fast5_fn] for _, pr in failed)
+        # spot check of what landed on disk
+        f = fast5_io.open_fast5(jobs[0][0], 'r')
+        ev = f['/Analyses/RawGenomeCorrected_000/BaseCalled_template/Events'][()]
+        f.close()
+        return {'value': ok_samples / dt, 'unit': UNIT, 'reads_per_s': (n - len(failed)) / dt, 'files': n,
+                'failed_reads': len(failed), 'seconds': dt, 'io_procs': fast5_jobs.io_procs(),
+                'bytes_per_file_in': int(np.mean(sizes)), 'events_rows_file0': int(len(ev)),
+                'setup_seconds': setup_s,
+                'what': 'resquiggle_reads_batch: FAST5 open + raw signal read, device batch, RawGenomeCorrected '
+                        'write-back into the same file (hdf5_min.py, gzip level 4); mapper and basecall '
+                        'event parsing not included'}
+    finally:
+        fast5_jobs.shutdown()
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def cpu_baseline_leg(args, reads):
     cores = host_cores()
     n = min(len(reads), max(8, 8 * cores if args.cpu_reads is None else args.cpu_reads))
@@ -500,6 +561,8 @@ def main():
     ap.add_argument('--cpu-reads', type=int, default=None)
     ap.add_argument('--ref-reads', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--fast5-files', type=int, default=1024,
+                    help='FAST5 files on disk for the e2e_fast5 leg (N = 1 only; 0 = skip)')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

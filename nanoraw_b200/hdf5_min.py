@@ -547,6 +547,21 @@ class Reader(object):
                 sel_src = tuple(slice(0, sl.stop - sl.start) for sl in sel_dst)
                 full[sel_dst] = block[sel_src]
             return full
+
+        def stored_chunk():
+            """the compressed bytes of a dataset held as one deflate chunk covering it, for verbatim re-writing"""
+            if [f[0] for f in filters] != [1] or tuple(cdims) != tuple(shape) or isinstance(dtype, VlenStr):
+                return None
+            chunks = []
+            if single is not None:
+                if single[2] is not None:
+                    chunks.append(((0,) * rank, single[0], single[1], single[2]))
+            elif btree is not None:
+                self._chunks_btree(btree, rank, chunks)
+            if len(chunks) != 1 or chunks[0][2] != 0:
+                return None
+            return bytes(d[chunks[0][3]:chunks[0][3] + chunks[0][1]])
+        load_chunked.stored_chunk = stored_chunk
         return dtype, shape, load_chunked, compression
 
 
@@ -693,14 +708,21 @@ class Writer(object):
         return self.alloc(head + body)
 
     def _dataset(self, ds):
-        val, dt, shape = _as_array(ds._data)
-        if isinstance(dt, VlenStr):
-            raise Unsupported('variable-length string dataset')
-        raw = val.tobytes()
+        comp = None
+        if getattr(ds, '_cache', 0) is None and hasattr(ds._loader, 'stored_chunk'):
+            comp = ds._loader.stored_chunk()  # untouched since it was read: its chunk is copied as it is
+        if comp is not None:
+            dt, shape, raw = ds.dtype, ds.shape, b''
+        else:
+            val, dt, shape = _as_array(ds._data)
+            if isinstance(dt, VlenStr):
+                raise Unsupported('variable-length string dataset')
+            raw = val.tobytes()
         msgs = [(0x01, 0, _ds_message(shape)), (0x03, 1, _dt_message(dt))]
         nelem = int(np.prod(shape, dtype=np.int64)) if shape else 1
         if ds.compression and nelem > 0 and shape != ():
-            comp = zlib.compress(raw, 4)
+            if comp is None:
+                comp = zlib.compress(raw, 4)
             caddr = self.alloc(comp)
             rank = len(shape)
             ksz = 8 + 8 * (rank + 1)

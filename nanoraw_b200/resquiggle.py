@@ -200,12 +200,17 @@ def resquiggle_reads_batch(
     FAST5 read -> one device batch (a1..a7) -> FAST5 write.  Returns [(error string, read)] for
     the reads that failed, with the reference's messages."""
     from .engine import ResquiggleParams, get_engine
+    from . import fast5_jobs
     failed = []
     ready = []
-    for pr in pending:
+    # FAST5 reads of the whole batch, on the I/O processes
+    loaded = fast5_jobs.map_jobs(fast5_jobs.read_job, [
+        (pr.fast5_fn, norm_type, basecall_group, pr.read_info.Subgroup) for pr in pending])
+    for pr, got in zip(pending, loaded):
         try:
-            chan, raw, ev_means, ev_kmers = _read_raw_inputs(
-                pr.fast5_fn, norm_type, basecall_group, pr.read_info.Subgroup)
+            if got[0] != 'ok':
+                raise NotImplementedError(got[1])
+            chan, raw, ev_means, ev_kmers = got[1:]
             pr.raw = np.ascontiguousarray(raw, dtype=np.int16)
             pr.given = nh.given_shift_scale(norm_type, chan, pore_model, ev_means, ev_kmers)
             ready.append(pr)
@@ -224,6 +229,7 @@ def resquiggle_reads_batch(
         compute_sd=compute_sd, num_cpts_limit=num_cpts_limit, timeout=timeout,
         min_event_obs=min_event_obs)
     res = engine.run_host(batcher, params)
+    writes, writers = [], []
     for r, pr in enumerate(ready):
         exc = exception_for(res.status[r])
         if exc is not None:
@@ -236,13 +242,18 @@ def resquiggle_reads_batch(
             if norm_type != 'median':
                 sv = (pr.given[0], pr.given[1], sv[2], sv[3])
             events = res.events_of(r)
-            write_new_fast5_group(
+            writes.append((
                 pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, res.new_segs_of(r),
                 events['base'].tobytes().decode(), pr.rows, pr.starts, None,
                 nh.scaleValues(*sv), corrected_group, pr.read_info.Subgroup, norm_type,
-                outlier_thresh, compute_sd, event_data=events)
+                outlier_thresh, compute_sd, events))
+            writers.append(pr)
         except Exception as e:  # noqa: BLE001
             failed.append((str(e), pr))
+    # RawGenomeCorrected write-back of the whole batch, on the I/O processes
+    for pr, err in zip(writers, fast5_jobs.map_jobs(fast5_jobs.write_job, writes)):
+        if err is not None:
+            failed.append((err, pr))
     return failed
 
 

@@ -16,6 +16,7 @@ noise and rare spikes.  The "basecaller" segmentation is the true one damaged
 by the alignment's indels (a deleted base loses its boundary, an inserted base
 splits a segment), which is the situation the re-squiggle repairs.
 """
+import os
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -351,3 +352,35 @@ def to_basecall_events(read, stay_rate=0.1, lead_stays=0, trail_stays=0, samplin
     ev['move'] = moves
     ev['move'][0] = 1
     return ev
+
+
+def write_basecalled_fast5_job(job):
+    """(file name, SynthRead) -> one basecalled single-read FAST5 file on disk, in the state prep_fast5 leaves it
+    (resquiggle.py:942-988); returns its size.  Module-level so that I/O processes can run it."""
+    fn, read = job
+    from . import fast5_io
+    f = fast5_io.open_fast5(fn, 'w')
+    rd = f.create_group('Raw/Reads/Read_1')
+    rd.create_dataset('Signal', data=read.raw, compression='gzip')
+    rd.attrs['read_id'] = read.read_id or os.path.basename(fn)
+    rd.attrs['start_time'] = np.uint64(0)
+    ch = f.create_group('UniqueGlobalKey/channel_id')
+    for k, v in (('offset', 10.0), ('range', 1400.0), ('digitisation', 8192.0), ('sampling_rate', 4000.0)):
+        ch.attrs[k] = np.float64(v)
+    ch.attrs['channel_number'] = '11'
+    f.create_group('Analyses/Basecall_1D_000').attrs['version'] = '1.1.0'
+    f.create_dataset('Analyses/Basecall_1D_000/BaseCalled_template/Events',
+                     data=to_basecall_events(read, seed=1), compression='gzip')
+    grp = f.create_group('Analyses/RawGenomeCorrected_000')  # what prep_fast5 leaves behind (resquiggle.py:942-988)
+    grp.attrs['nanoraw_version'] = '0.5'
+    grp.attrs['basecall_group'] = 'Basecall_1D_000'
+    f.close()
+    return os.path.getsize(fn)
+
+
+def drop_corrected_job(job):
+    """remove the corrected subgroup again (bench set-up between passes)"""
+    from . import fast5_io
+    f = fast5_io.open_fast5(job[0], 'r+')
+    del f['/Analyses/RawGenomeCorrected_000/BaseCalled_template']
+    f.close()
