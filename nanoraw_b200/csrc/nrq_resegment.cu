@@ -44,6 +44,7 @@ struct SegCtx {
   double* buf_big;
   int big_cap;
   const double* lut;  // normalised value of DAC code lut_lo + k
+  unsigned* picks;    // this warp's picks of one selection, in pick order (shared memory)
   int lut_lo;
 };
 
@@ -106,42 +107,68 @@ __device__ __forceinline__ unsigned warp_argmax(unsigned long long best, int bi)
   return __reduce_max_sync(kFull, c2 ? (unsigned)(bi + 1) : 0u);
 }
 
-// greedy selection (:244-254) with the keys held in registers: lane owns i = lane + 32 e, e < E.
+// greedy selection (:244-254) with the keys held in registers: lane owns i = lane + 32 e, e < E.  A key is the
+// bit pattern of the running difference split in two words, the high one + 1 so that 0 there means "not a
+// candidate" (out of range or blacklisted) whatever the low word holds.  Each round's pick goes to `picks`
+// (shared memory, one store by lane 0); the sorted output is formed once at the end from a bitmap of the picks.
 // 1: K change-points written in ascending order; 0: None.
 template <int E>
 __device__ __forceinline__ int select_cpts_regs(const SegCtx& c, const double* cs, int nrd, int K, int t0,
-                                                int outpos) {
+                                                int outpos, unsigned* picks) {
   const int lane = (int)lane_id();
   const int m = c.m;
-  unsigned long long key[E];  // bits(rd) + 1 while the position is still a candidate, 0 once it is not
-  unsigned picked = 0;        // bit e: position lane + 32 e was chosen
+  unsigned kh[E], kl[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    int i = lane + 32 * e;
-    key[e] = i < nrd ? rd_key(cs, i, m) - 1ull : 0ull;
+    const int i = lane + 32 * e;
+    kh[e] = 0u;
+    kl[e] = 0u;
+    if (i < nrd) {
+      const unsigned long long k = rd_key(cs, i, m) - 2ull;  // the bit pattern itself
+      kh[e] = (unsigned)(k >> 32) + 1u;
+      kl[e] = (unsigned)k;
+    }
   }
   for (int round = 0; round < K; ++round) {
-    unsigned long long best = 0;
-    int bi = -1;
+    // this lane's best candidate; strict compares from the top, so the larger index wins ties
+    unsigned bh = kh[E - 1], bl = kl[E - 1];
+    int bi1 = lane + 32 * (E - 1) + 1;
 #pragma unroll
-    for (int e = E - 1; e >= 0; --e)  // descending + strict: the larger index wins ties
-      if (key[e] > best) { best = key[e]; bi = lane + 32 * e; }
-    unsigned mi = warp_argmax(best, bi);
-    if (mi == 0u) return 0;  // fewer than K placeable: None (:253-254)
-    const int p = (int)mi - 1;
-    if (bi == p) picked |= 1u << (bi >> 5);  // only the owning lane's candidate can be p
+    for (int e = E - 2; e >= 0; --e) {
+      const bool g = kh[e] > bh || (kh[e] == bh && kl[e] > bl);
+      bh = g ? kh[e] : bh;
+      bl = g ? kl[e] : bl;
+      bi1 = g ? lane + 32 * e + 1 : bi1;
+    }
+    const unsigned mh = __reduce_max_sync(kFull, bh);
+    if (mh == 0u) return 0;  // fewer than K placeable: None (:253-254)
+    const bool c1 = bh == mh;
+    const unsigned ml = __reduce_max_sync(kFull, c1 ? bl : 0u);
+    const bool c2 = c1 && bl == ml;
+    const int p = (int)__reduce_max_sync(kFull, c2 ? (unsigned)bi1 : 0u) - 1;
+    if (lane == 0) picks[round] = (unsigned)p;
 #pragma unroll
     for (int e = 0; e < E; ++e)  // blacklist p-m+1 .. p+m (:249-250)
-      if ((unsigned)(lane + 32 * e - (p - m + 1)) < (unsigned)(2 * m)) key[e] = 0ull;
+      if ((unsigned)(lane + 32 * e - (p - m + 1)) < (unsigned)(2 * m)) kh[e] = 0u;
   }
-  // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275)
+  __syncwarp();
+  // sorted(cpt + min_seg_len) + align_segs[group_start]  (:255, :275): bit i of the bitmap = position i picked
+  unsigned word[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) word[e] = 0u;
+#pragma unroll 1
+  for (int base = 0; base < K; base += 32) {  // K <= 64: at most two passes
+    const unsigned pr = base + lane < K ? picks[base + lane] : 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      word[e] |= __reduce_or_sync(kFull, (pr >> 5) == (unsigned)e ? 1u << (pr & 31u) : 0u);
+  }
   int cnt = 0;
 #pragma unroll
   for (int e = 0; e < E; ++e) {
-    bool f = (picked >> e) & 1u;
-    unsigned bal = __ballot_sync(kFull, f);
-    if (f) c.out[outpos + cnt + __popc(bal & ((1u << lane) - 1u))] = t0 + lane + 32 * e + m;
-    cnt += __popc(bal);
+    if ((word[e] >> lane) & 1u)
+      c.out[outpos + cnt + __popc(word[e] & ((1u << lane) - 1u))] = t0 + lane + 32 * e + m;
+    cnt += __popc(word[e]);
   }
   return 1;
 }
@@ -198,7 +225,7 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
   const int nrd = n - 2 * m + 1;  // len(running_diffs)
   if (nrd <= 0) return 0;
   const int16_t* s = c.sig + t0;
-  if (n <= kRegionCap) {
+  if (n <= kRegionCap && K <= 64) {  // (64: capacity of the per-warp pick list)
     // shared memory: buf[1] = cs[0] = 0, buf[2 + j] = x[j] then cs[j + 1]; pairs are 16-byte aligned
     double* buf = c.buf_sm;
     if (c.xsig) for (int j = lane; j < n; j += 32) buf[2 + j] = c.xsig[t0 + j];
@@ -232,10 +259,10 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
     __syncwarp();
     const double* cs = buf + 1;
     int res;
-    if (nrd <= 32) res = select_cpts_regs<1>(c, cs, nrd, K, t0, outpos);
-    else if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos);
-    else if (nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos);
-    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos);
+    if (nrd <= 32) res = select_cpts_regs<1>(c, cs, nrd, K, t0, outpos, c.picks);
+    else if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos, c.picks);
+    else if (kRegionCap <= 135 || nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos, c.picks);
+    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos, c.picks);
     __syncwarp();
     return res;
   }
@@ -394,6 +421,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
   struct WarpSm {
     double region[kRegionCap + 2];
     double lut[kSegLut];
+    unsigned picks[64];  // picks are at least min_seg_len apart and the region holds <= 254 samples
   };
   __shared__ __align__(16) WarpSm sm[kSegWarps];
   const int warp = threadIdx.x >> 5;
@@ -431,6 +459,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.buf_sm = my.region;
     // table of normalised values over the codes that survive clipping (or around a pivot sample)
     c.lut = my.lut;
+    c.picks = my.picks;
     c.lut_lo = (g.xsig ? 0 : (int)g.sig[g.n_norm / 2]) - kSegLut / 2;
     if (c.coef.clip) {
       double e0 = c.coef.shift + c.coef.lo * c.coef.scale, e1 = c.coef.shift + c.coef.hi * c.coef.scale;
