@@ -405,14 +405,14 @@ def gpu_arm(args):
 def measured_traffic(args, kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
     `ncu --set full` capture of this same workload (profiles/), or None when the workload differs."""
-    path = os.path.join(ROOT, 'profiles', 'r1r_traffic_100k.json')
+    path = os.path.join(ROOT, 'profiles', 'r1s_traffic_100k.json')
     if not (os.path.exists(path) and args.reads == 100_000 and args.config == 'standard'):
         return None, None
     data = json.load(open(path))['kernels']
     names = {'k_align_scan': ('k_align_count', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
              'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}[kernel]
     total = sum(data[n]['dram_read_bytes'] + data[n]['dram_write_bytes'] for n in names)
-    return int(total), 'profiles/r1r_traffic_100k.json (ncu --set full, same workload)'
+    return int(total), 'profiles/r1s_traffic_100k.json (ncu --set full, same workload)'
 
 
 def algorithmic_bytes(t):
