@@ -280,12 +280,11 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
   return select_cpts_mem(c, buf, nrd, K, t0, outpos);
 }
 
-// extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
-__device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
-  int K, t_start, t_stop;  // t[start], t[stop] of the current (start, stop)
-  int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
-  if (st != NRQ_ST_OK) return st;
-  st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
+// extend_for_cpts (:256-276) for a group whose extend_group result is already known, preceded by the merge
+// loop of extend_and_join (:220-225)
+__device__ __forceinline__ int search_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop,
+                                            int K, int t_start, int t_stop) {
+  int st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
   if (st != NRQ_ST_OK) return st;
   for (;;) {
     int res = get_cpts(c, t_start, t_stop, K, start + c.ind[lo].w + 1);
@@ -300,6 +299,14 @@ __device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxe
     st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
     if (st != NRQ_ST_OK) return st;
   }
+}
+
+// extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
+__device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
+  int K, t_start, t_stop;  // t[start], t[stop] of the current (start, stop)
+  int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
+  if (st != NRQ_ST_OK) return st;
+  return search_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
 }
 
 __device__ __forceinline__ long long global_ns() {
@@ -356,40 +363,131 @@ __device__ int splice_and_validate(const SegCtx& c, int n_bases, int n_norm, int
   return NRQ_ST_OK;
 }
 
-__device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm, int& region_samples) {
-  const unsigned lane = lane_id();
-  const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
-  if (c.n_ind > 0) {
-    int lo = 0, hi = 0, maxend = c.ind[0].y;
-    int start, stop;
-    int4 ahead = c.n_ind > 1 ? c.ind[1] : make_int4(0, 0, 0, 0);
-    for (int k = 1; k < c.n_ind; ++k) {
-      if (timeout_ns > 0 && global_ns() - t_begin > timeout_ns) return NRQ_ST_TIMEOUT;  // :288-289
-      const int4 nxt = ahead;
-      if (k + 1 < c.n_ind) ahead = c.ind[k + 1];
-      if (maxend >= nxt.x) {  // :291-292
-        hi = k;
-        maxend = max(maxend, nxt.y);
-        continue;
-      }
-      int st = close_group(c, lo, hi, maxend, start, stop);
-      if (st != NRQ_ST_OK) return st;
-      if (stop >= nxt.x) {  // :299-300
-        hi = k;
-        maxend = max(maxend, nxt.y);
-      } else {  // :302-304
-        if (lane == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
-        __syncwarp();
-        ++c.ng;
-        lo = hi = k;
-        maxend = nxt.y;
-      }
+__device__ __forceinline__ void push_group(SegCtx& c, int start, int stop, int lo, int maxend) {
+  if (lane_id() == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
+  __syncwarp();
+  ++c.ng;
+}
+
+// The driver loop of get_indel_groups (:286-314), indel by indel, from a group (lo .. hi, maxend) that is still
+// open and indel k as the next one to look at, until that group has been finished and pushed.  On return k is the
+// first indel of the next group (n_ind when the read's last group was pushed).
+__device__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend) {
+  int start, stop;
+  for (; k < c.n_ind; ++k) {
+    const int4 nxt = c.ind[k];
+    if (maxend >= nxt.x) {  // :291-292
+      hi = k;
+      maxend = max(maxend, nxt.y);
+      continue;
     }
-    int st = close_group(c, lo, hi, maxend, start, stop);  // :307-314
+    int st = close_group(c, lo, hi, maxend, start, stop);
     if (st != NRQ_ST_OK) return st;
-    if (lane == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
+    if (stop >= nxt.x) {  // :299-300
+      hi = k;
+      maxend = max(maxend, nxt.y);
+      continue;
+    }
+    push_group(c, start, stop, lo, maxend);  // :302-304
+    return NRQ_ST_OK;
+  }
+  int st = close_group(c, lo, hi, maxend, start, stop);  // :307-314
+  if (st != NRQ_ST_OK) return st;
+  push_group(c, start, stop, lo, maxend);
+  return NRQ_ST_OK;
+}
+
+constexpr int kPlanGeneric = 15;       // record status: take the indel-by-indel path for this group
+constexpr int kPlanKBits = 22;         // a record packs K (22 bits), the group's last lane (5) and a status (4)
+
+// get_indel_groups (:278-316).  The grouping of indels by touching padded spans (:291-292) and the first
+// extend_group of each group (:203-216) do not depend on how earlier groups fared, so they are worked out for the
+// next 32 indels at once, one lane per indel: a running maximum of the indel ends (warp scan) marks where groups
+// break, and the lane of each group's first indel grows the group until it can hold its change-points.  Each
+// finished plan is a 16-byte record parked in the read's group scratch at the index of the group's first indel
+// (the stack of finished groups never reaches that far: it holds at most one entry per consumed indel).  The warp
+// then walks the planned groups in order and does what the reference does for each: merge with finished groups it
+// runs into, search, retry; a group that ends up reaching the next indel (:299-300), or that does not fit the
+// 32-indel window, is carried on indel by indel (drive_until_push) and planning resumes behind it.
+__device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm, int& region_samples) {
+  const int lane = (int)lane_id();
+  const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
+  int k = 0;  // first indel that is not part of a finished group
+  while (k < c.n_ind) {
+    if (timeout_ns > 0 && global_ns() - t_begin > timeout_ns) return NRQ_ST_TIMEOUT;  // :288-289
+    // ---- plan the groups among indels k .. k + 31
+    const bool valid = k + lane < c.n_ind;
+    int4 my = make_int4(0x7fffffff, 0, 0, 0);  // past the last indel: always starts a group, i.e. ends the one before
+    if (valid) my = c.ind[k + lane];
+    int M = my.y;  // running maximum of the ends: equals the open group's own maximum wherever it matters
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(kFull, M, o);
+      if (lane >= o) M = max(M, t);
+    }
+    const int m_prev = __shfl_up_sync(kFull, M, 1);
+    const bool brk = lane == 0 || m_prev < my.x;
+    const unsigned heads = __ballot_sync(kFull, brk);
+    const unsigned after = lane == 31 ? 0u : heads >> (lane + 1);
+    const bool complete = after != 0u;                       // the group's end lies inside the window
+    const int e = complete ? lane + __ffs(after) - 1 : lane;  // lane of the group's last indel
+    const int gmax = __shfl_sync(kFull, M, e);
+    const int zsum = __shfl_sync(kFull, my.w + my.z, e);
+    const bool planned = brk && valid && complete;
+    if (planned) {  // extend_group (:203-216) for the group lane .. e
+      int start = my.x, stop = gmax, st = NRQ_ST_OK;
+      int K = (zsum - my.w) + stop - start - 1;
+      if (start < 0 || stop > c.last) st = NRQ_ST_BAD_ALIGNMENT;
+      while (st == NRQ_ST_OK) {
+        if (c.t[stop] - c.t[start] >= (K + 2) * c.m) break;
+        if (start == 0 && stop == c.last) { st = NRQ_ST_UNSATISFIABLE; break; }
+        K += (start > 0) + (stop < c.last);
+        start = max(0, start - 1);
+        stop = min(c.last, stop + 1);
+      }
+      if (K < 0 || K >= (1 << kPlanKBits)) { st = kPlanGeneric; K = 0; }
+      c.groups[k + lane] = make_int4(start, stop, K | ((e - lane) << kPlanKBits) | (st << (kPlanKBits + 5)), gmax);
+    }
+    unsigned todo = __ballot_sync(kFull, planned);
     __syncwarp();
-    ++c.ng;
+    if (todo == 0u) {  // more than 32 indels in one group
+      int kk = k + 1;
+      int st = drive_until_push(c, kk, k, k, c.ind[k].y);
+      if (st != NRQ_ST_OK) return st;
+      k = kk;
+      continue;
+    }
+    // ---- walk the planned groups
+    int next_k = k;
+    while (todo) {
+      const int s = __ffs(todo) - 1;
+      todo &= todo - 1;
+      int lo = k + s;
+      const int4 rec = c.groups[lo];
+      const int hi = lo + ((rec.z >> kPlanKBits) & 31);
+      int st = (rec.z >> (kPlanKBits + 5)) & 15;
+      int start = rec.x, stop = rec.y, maxend = rec.w;
+      if (st == kPlanGeneric) {
+        st = close_group(c, lo, hi, maxend, start, stop);
+      } else {
+        if (st != NRQ_ST_OK) return st;
+        st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop]);
+      }
+      if (st != NRQ_ST_OK) return st;
+      if (hi + 1 < c.n_ind) {
+        const int4 nxt = c.ind[hi + 1];
+        if (stop >= nxt.x) {  // :299-300: the finished group reaches the next indel and stays open
+          int kk = hi + 2;
+          st = drive_until_push(c, kk, lo, hi + 1, max(maxend, nxt.y));
+          if (st != NRQ_ST_OK) return st;
+          next_k = kk;
+          break;  // plans made behind this point may no longer hold
+        }
+      }
+      push_group(c, start, stop, lo, maxend);
+      next_k = hi + 1;
+    }
+    k = next_k;
   }
   return splice_and_validate(c, n_bases, n_norm, region_samples);
 }
