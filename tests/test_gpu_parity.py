@@ -214,6 +214,50 @@ def test_seeded_reads_against_oracle(engine, name, exact_stats):
             assert np.max(np.abs(ev['norm_stdev'] - out['events']['norm_stdev'])) < 1e-12
 
 
+def handmade_read(units, seed, dwell=18, lead=40, tail=40):
+    """a read whose alignment is `lead` matches, then `units` (strings over M / I / D, one alignment column
+    each: match, base only in the read, base only in the genome), then `tail` matches"""
+    rng = np.random.default_rng(seed)
+    ops = 'M' * lead + ''.join(units) + 'M' * tail
+    acgt = np.frombuffer(b'ACGT', dtype=np.uint8)
+    read_row = np.where(np.array(list(ops)) == 'D', ord('-'), acgt[rng.integers(0, 4, len(ops))]).astype(np.uint8)
+    genome_row = np.where(np.array(list(ops)) == 'I', ord('-'), acgt[rng.integers(0, 4, len(ops))]).astype(np.uint8)
+    n_read = int((read_row != ord('-')).sum())
+    dwells = rng.integers(dwell - 6, dwell + 7, n_read)
+    starts = np.concatenate([[0], np.cumsum(dwells)]).astype(np.int64)
+    levels = rng.normal(500, 60, n_read)
+    raw = np.rint(np.repeat(levels, dwells) + rng.normal(0, 12, int(starts[-1]))).astype(np.int16)
+    pre = rng.integers(300, 700, 25).astype(np.int16)
+    return synth.SynthRead(raw=np.concatenate([pre, raw, pre]), read_start_rel_to_raw=25, starts=starts,
+                           read_align=read_row.tobytes(), genome_align=genome_row.tobytes())
+
+
+def test_groups_larger_than_the_planning_window(engine):
+    """k_resegment plans indel groups 32 indels at a time: groups of more than 32 indels, groups that end exactly
+    at a window edge and long chains of absorbed groups must come out as in the oracle"""
+    from nanoraw_b200.engine import ResquiggleParams
+    reads = [
+        handmade_read(['MI', 'MD'] * 45, 1),                                  # one group of 90 indels
+        handmade_read((['MI'] * 31 + ['M' * 12]) * 3 + ['MD'] * 33, 2),       # 31-, 31-, 31- and 33-indel groups
+        handmade_read((['MMI'] * 8 + ['M' * 9]) * 12, 3),                     # 8-indel groups, 4 per window
+        handmade_read(['MMMI', 'MMMD'] * 60, 4, dwell=9),                     # isolated indels that merge on retry
+        handmade_read(['I' * 3 + 'M', 'D' * 2 + 'M'] * 40, 5, dwell=24),      # long runs, one open-ended group
+        handmade_read(['MMMMMI', 'MMMMMMD'] * 40, 6, dwell=7),                # short dwell: retries and merges
+    ]
+    res = engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+    for r, read in enumerate(reads):
+        try:
+            out = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                                      read.read_align.decode(), read.genome_align.decode())
+        except orc.RegionUnsatisfiable:
+            from nanoraw_b200 import _lib
+            assert res.status[r] == _lib.ST_UNSATISFIABLE, r
+            continue
+        assert res.ok(r), (r, res.error(r))
+        assert np.array_equal(res.new_segs_of(r), out['new_segs']), r
+        assert close(res.events_of(r)['norm_mean'], out['events']['norm_mean'])
+
+
 def test_unsatisfiable_region_terminates(engine):
     """mean dwell <= 5 samples/base: the reference loops forever (resquiggle.py:210-215);
     the device path must stop with NRQ_ST_UNSATISFIABLE like the oracle's guard."""
