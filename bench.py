@@ -264,6 +264,9 @@ def gpu_arm(args):
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if world > 1:
         torch.cuda.set_device(local)
+        # stdout carries the one JSON line and nothing else: NCCL's own messages (its version banner under
+        # NCCL_DEBUG=VERSION/WARN/INFO) go to stderr
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     else:
         torch.cuda.set_device(0)

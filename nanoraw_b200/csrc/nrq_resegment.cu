@@ -37,6 +37,7 @@ struct SegCtx {
   int n_ind;
   int4* groups;       // finished groups: (start, stop, first indel, max indel end)
   int ng;
+  int top_stop;       // groups[ng - 1].y, or -1: what a new group is checked against (:220, :267)
   int32_t* out;       // new_segs
   int m;              // min_seg_len
   int limit;          // cpts limit or < 0
@@ -70,10 +71,10 @@ __device__ __forceinline__ int extend_group(const SegCtx& c, int lo, int hi, int
 // the merge loop shared by extend_and_join (:220-225) and extend_for_cpts (:267-272)
 __device__ __forceinline__ int swallow_previous(SegCtx& c, int& lo, int hi, int& maxend,
                                                 int& start, int& stop, int& K, int& t_start, int& t_stop) {
-  while (c.ng > 0) {
+  while (start <= c.top_stop) {  // top_stop: stop of the last finished group, -1 when there is none
     int4 prev = c.groups[c.ng - 1];
-    if (start > prev.y) break;
     --c.ng;
+    c.top_stop = c.ng > 0 ? c.groups[c.ng - 1].y : -1;
     lo = prev.z;
     maxend = max(maxend, prev.w);
     int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
@@ -367,6 +368,7 @@ __device__ __forceinline__ void push_group(SegCtx& c, int start, int stop, int l
   if (lane_id() == 0) c.groups[c.ng] = make_int4(start, stop, lo, maxend);
   __syncwarp();
   ++c.ng;
+  c.top_stop = stop;
 }
 
 // The driver loop of get_indel_groups (:286-314), indel by indel, from a group (lo .. hi, maxend) that is still
@@ -547,6 +549,7 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.n_ind = (int)(indel_off[r + 1] - indel_off[r]);
     c.groups = group_scratch + indel_off[r];
     c.ng = 0;
+    c.top_stop = -1;
     c.out = new_segs + b.align_off[r] + r;
     // the two pointers the state machine dereferences most are pinned in vector registers; as warp-uniform
     // values the compiler otherwise re-forms their addresses on the uniform datapath at every use (4 instructions)
