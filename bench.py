@@ -39,6 +39,24 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_JSON_OUT = [None]
+
+
+def claim_stdout():
+    """stdout carries the one JSON line and nothing else: keep a private handle on it and point fd 1 at stderr,
+    so that whatever a library prints (NCCL's version banner, warnings of child processes) cannot get in"""
+    if _JSON_OUT[0] is None:
+        sys.stdout.flush()
+        _JSON_OUT[0] = os.fdopen(os.dup(1), 'w')
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT[0] or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
+
+
 def host_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -116,7 +134,7 @@ def reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args):
@@ -399,7 +417,7 @@ def gpu_arm(args):
             line['cpu_baseline'] = cpu_baseline_leg(args, reads)
         if world == 1 and args.fast5_files > 0:
             line['e2e_fast5'] = fast5_leg(args, reads)
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -567,6 +585,7 @@ def main():
     ap.add_argument('--fast5-files', type=int, default=1024,
                     help='FAST5 files on disk for the e2e_fast5 leg (N = 1 only; 0 = skip)')
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == 'reference':
         reference_arm(args)
     else:
