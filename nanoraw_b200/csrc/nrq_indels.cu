@@ -184,6 +184,8 @@ k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __r
   // lane-0 broadcast: marks r (and what is loaded through it) warp-uniform for the compiler
   int r = blockIdx.x * kWarpsPerCta + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
+  __shared__ __align__(16) uint8_t stage[kWarpsPerCta][512 + 48];  // one step's genome bases, see below
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   const unsigned lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
   int64_t a0 = b.align_off[r];
@@ -232,21 +234,35 @@ k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __r
       int k = 0;
       for (unsigned todo = sany; todo; todo &= todo - 1u, ++k) {
         const int i = __ffs(todo) - 1;
-        int4* o = out + run0 + k;
-        o->x = col0 + i;
-        o->z = r0 + __popc(rmask & ((1u << i) - 1u));
-        o->w = (int)((sr >> i) & 1u);
+        // one 16-byte store; the end column (.y) comes from whichever lane sees the run end, possibly a later step
+        out[run0 + k] = make_int4(col0 + i, 0, r0 + __popc(rmask & ((1u << i) - 1u)), (int)((sr >> i) & 1u));
       }
+      __syncwarp();  // a run may start in one lane and end in the next: starts before ends
       for (unsigned todo = eany; todo; todo &= todo - 1u) {
         const int i = __ffs(todo) - 1;
         out[run0 + __popc(sany & ((1u << i) - 1u)) - 1].y = col0 + i;
       }
       if (bases) {
-        uint8_t* dst = bases + gbase + (int)(ex >> 20);
+        // genome bases of this step, gaps squeezed out: each lane packs its own into shared memory, placed so that
+        // 16-byte chunks of the staging buffer line up with 16-byte chunks of the output, then the warp copies
+        // whole chunks with 128-bit stores (scattered byte stores to global cost a sector each)
+        uint8_t* const dst0 = bases + gbase;
+        const int lo = (int)((uintptr_t)dst0 & 15u), hi = lo + (int)(tot >> 20);
+        uint8_t* sh = stage[warp] + lo + (int)(ex >> 20);
         const unsigned w[4] = {c.g.x, c.g.y, c.g.z, c.g.w};
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if ((gmask >> i) & 1u) *dst++ = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+          if ((gmask >> i) & 1u) *sh++ = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+        __syncwarp();
+        const int first_full = (lo + 15) >> 4, last_full = hi >> 4;  // whole chunks [first_full, last_full)
+        for (int ch = first_full + (int)lane; ch < last_full; ch += 32)
+          *reinterpret_cast<uint4*>(dst0 - lo + 16 * ch) = *reinterpret_cast<const uint4*>(stage[warp] + 16 * ch);
+        const int head_end = min(16 * first_full, hi);
+        int j = lo + (int)lane;
+        if (j < head_end) dst0[j - lo] = stage[warp][j];
+        j = max(16 * last_full, head_end) + (int)lane;
+        if (j < hi) dst0[j - lo] = stage[warp][j];
+        __syncwarp();
       }
       idx_base += (int)(tot & 1023u);
       rbase += (int)((tot >> 10) & 1023u);
@@ -299,10 +315,17 @@ k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __r
       int len = e - s;
       const uint8_t* seq = (ins ? ga : ra) + s;  // :160-164
       int n_before = s - prev_end, n_after = next_start - e;
-      int d = 0;
-      while (d < n_after - 1 && seq[d % len] == ga[e + d]) ++d;          // :188-190
-      int u = -1;
-      while (-u <= n_before - 1 && seq[pymod(u, len)] == ga[s + u]) --u;  // :191-193
+      // seq[d % len] and seq[u mod len] walk the run cyclically: indices kept by stepping, no division
+      int d = 0, jd = 0;
+      while (d < n_after - 1 && seq[jd] == ga[e + d]) {                   // :188-190
+        ++d;
+        if (++jd == len) jd = 0;
+      }
+      int u = -1, ju = len - 1;
+      while (-u <= n_before - 1 && seq[ju] == ga[s + u]) {                // :191-193
+        --u;
+        if (--ju < 0) ju = len - 1;
+      }
       start = crl + u;
       end = (ins ? crl + 1 : crl + len + 1) + d;                          // :178-179
       diff = ins ? len : -len;                                             // :180
