@@ -394,7 +394,8 @@ def gpu_arm(args):
                     'peak_source': peak_src, 'share_of_step': stages[dom]['ms'] / float(stage_ms.sum()),
                     'stages': stages,
                     'path': {'algorithmic_bytes': stage_bytes['path'], 'achieved': path_gbs,
-                             'frac': path_gbs / peak}}
+                             'frac': path_gbs / peak},
+                    'issue': issue_figures(args, stages, clocks)}
         line = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_per_step, 'higher_is_better': True,
@@ -423,17 +424,45 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-def measured_traffic(args, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
-    `ncu --set full` capture of this same workload (profiles/), or None when the workload differs."""
-    path = os.path.join(ROOT, 'profiles', 'r1s_traffic_100k.json')
+TRAFFIC_FILE = 'r1u_traffic_100k.json'
+STAGE_KERNELS = {'k_align_scan': ('k_align_count', 'k_scan_counts', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
+                 'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}
+
+
+def ncu_capture(args):
+    """per-kernel figures of the committed `ncu --set full` capture of this same workload (profiles/), or None
+    when the workload differs"""
+    path = os.path.join(ROOT, 'profiles', TRAFFIC_FILE)
     if not (os.path.exists(path) and args.reads == 100_000 and args.config == 'standard'):
+        return None
+    return json.load(open(path))['kernels']
+
+
+def measured_traffic(args, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`"""
+    data = ncu_capture(args)
+    if data is None:
         return None, None
-    data = json.load(open(path))['kernels']
-    names = {'k_align_scan': ('k_align_count', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
-             'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}[kernel]
-    total = sum(data[n]['dram_read_bytes'] + data[n]['dram_write_bytes'] for n in names)
-    return int(total), 'profiles/r1s_traffic_100k.json (ncu --set full, same workload)'
+    total = sum(data[n]['dram_read_bytes'] + data[n]['dram_write_bytes'] for n in STAGE_KERNELS[kernel] if n in data)
+    return int(total), 'profiles/%s (ncu --set full, same workload)' % TRAFFIC_FILE
+
+
+def issue_figures(args, stages, clocks):
+    """The stages are bound by instruction issue rather than by DRAM: warp instructions per launch (ncu capture of
+    the same workload) over the stage's CUDA-event time, against 4 schedulers x 1 instruction / clock per SM."""
+    data = ncu_capture(args)
+    if data is None or not clocks.get('sm_mhz'):
+        return None
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    peak = sms * 4 * clocks['sm_mhz'] * 1e6
+    out = {'peak_warp_inst_per_s': peak, 'sms': sms, 'sm_mhz': clocks['sm_mhz'], 'stages': {}}
+    for name, st in stages.items():
+        inst = sum(data[n].get('warp_instructions', 0) for n in STAGE_KERNELS[name] if n in data)
+        if inst and st['ms'] > 0:
+            rate = inst / (st['ms'] * 1e-3)
+            out['stages'][name] = {'warp_instructions': inst, 'achieved': rate, 'frac': rate / peak}
+    return out
 
 
 def algorithmic_bytes(t):
