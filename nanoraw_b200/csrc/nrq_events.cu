@@ -160,7 +160,10 @@ k_event_table_exact(nrq_batch b, nrq_params p, const double* __restrict__ sv, co
 // coalesced, with no per-base loops.  The numerator n_u S2 - S1^2 is formed in 128-bit integers:
 // no cancellation.  Results differ from numpy's (which sums the individually rounded x_i) by a few
 // ulps -- far inside the 1e-9 contract -- and are checked against the exact kernel in tests.
-constexpr int kEvWarps = 8;   // reads per CTA: one warp streams one read
+#ifndef NRQ_EV_WARPS
+#define NRQ_EV_WARPS 2
+#endif
+constexpr int kEvWarps = NRQ_EV_WARPS;   // reads per CTA: one warp streams one read; small CTAs, so that few warps idle while the longest read of a CTA finishes (8 / 4 / 2 warps: 13.8 / 13.6 / 13.5 ms)
 constexpr int kSub = 32 * 8;  // samples per step: one 128-bit load per lane
 
 struct EvClass {
@@ -282,7 +285,7 @@ __device__ __forceinline__ EvClass ev_classify(const NormCoef& coef, int pivot_s
 }
 
 #ifndef NRQ_EV_MINB
-#define NRQ_EV_MINB 6
+#define NRQ_EV_MINB 24
 #endif
 
 // one step of the inclusive warp scan of (a, b): the shuffle's own predicate says whether lane - o exists, so
@@ -323,7 +326,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   __shared__ double rcp_tab[64];
   __shared__ EvLoc loc[kEvWarps][32];                          // lane-local exclusive prefixes of (d, d^2)
   __shared__ __align__(16) unsigned locc[kEvWarps][2][32][4];  // ... and of the packed clip counters
-  if (threadIdx.x < 64) rcp_tab[threadIdx.x] = threadIdx.x ? 1.0 / (double)threadIdx.x : 0.0;
+  for (int i = threadIdx.x; i < 64; i += kEvWarps * 32) rcp_tab[i] = i ? 1.0 / (double)i : 0.0;
   __syncthreads();
   // broadcast from lane 0: tells the compiler that the warp index and everything loaded through it are
   // warp-uniform, so the shuffles and votes below need no convergence barriers around them
