@@ -13,7 +13,10 @@
 
 namespace nrq {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef NRQ_K0_WARPS
+#define NRQ_K0_WARPS 8
+#endif
+constexpr int kWarpsPerCta = NRQ_K0_WARPS;  // one read per warp
 
 struct ColMasks {
   unsigned mr, mg, valid;
