@@ -19,13 +19,19 @@ from .frontend import alignment_worker
 ALIGN_BATCH_MULTIPLIER = 5  # parsed reads allowed to wait for the GPU, in alignment batches (:27)
 
 
-def _gpu_worker(device_index, worker_args):
+def _gpu_worker(device_index, worker_args, n_workers=1):
     import torch
-    from . import resquiggle
+    from . import fast5_jobs, resquiggle
     resquiggle.VERBOSE = worker_args[-1]
     if torch.cuda.is_available():
         torch.cuda.set_device(device_index % torch.cuda.device_count())
-    resquiggle.resquiggle_worker(*worker_args[:-1])
+    # the host cores are shared between the GPU workers' FAST5 I/O pools
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    os.environ.setdefault('NRQ_IO_PROCS', str(max(1, min(32, cores // max(n_workers, 1)))))
+    try:
+        resquiggle.resquiggle_worker(*worker_args[:-1])
+    finally:
+        fast5_jobs.shutdown()
 
 
 def _drain(q, into):
@@ -61,7 +67,7 @@ def resquiggle_all_reads(
     worker_args = (basecalls_q, failed_reads_q, basecall_group, corrected_group, norm_type,
                    outlier_thresh, timeout, num_cpts_limit, compute_sd, pore_model,
                    resquiggle.VERBOSE)
-    squigglers = [ctx.Process(target=_gpu_worker, args=(i, worker_args))
+    squigglers = [ctx.Process(target=_gpu_worker, args=(i, worker_args, num_resquiggle_ps))
                   for i in range(num_resquiggle_ps)]
     for p in aligners + squigglers:
         p.start()

@@ -375,3 +375,71 @@ def test_refuses_what_it_cannot_represent(tmp_path, native):
     del f['v'].attrs['big']
     f.close()
     assert fast5_io.open_fast5(str(tmp_path / 'x.fast5'), 'r')['v'][()].tolist() == [0, 1, 2]
+
+
+def test_reader_handles_new_style_structures():
+    """superblock 2, version-2 object headers with creation-order tracking and a continuation block, link messages
+    (compact group), dataspace v2, attribute v3, compact and single-chunk (layout v4) datasets: none of which the
+    writer emits.  The bytes are laid out here by hand from the format specification (checksums are not verified
+    by the reader and are left zero)."""
+    import zlib
+    buf = bytearray(48)  # superblock v2 goes in last
+
+    def put(b):
+        while len(buf) % 8:
+            buf.append(0)
+        a = len(buf)
+        buf.extend(b)
+        return a
+
+    def msg(mtype, body, track=False):
+        return struct.pack('<BHB', mtype, len(body), 0) + (b'\x00\x00' if track else b'') + body
+
+    def ohdr(msgs, flags=0):
+        body = b''.join(msgs)
+        head = b'OHDR' + bytes([2, flags])
+        if flags & 0x20:
+            head += b'\x00' * 16
+        if flags & 0x10:
+            head += struct.pack('<HH', 8, 6)
+        size_field = {0: '<B', 1: '<H', 2: '<I'}[flags & 3]
+        return head + struct.pack(size_field, len(body)) + body + b'\x00' * 4
+
+    f64 = struct.pack('<BBBBIHHBBBBI', 0x11, 0x20, 63, 0, 8, 0, 64, 52, 11, 0, 52, 1023)
+    i16 = struct.pack('<BBBBIHH', 0x10, 0x08, 0, 0, 2, 0, 16)
+    space1 = struct.pack('<BBBBQ', 2, 1, 0, 1, 5)            # dataspace v2, simple, rank 1, 5 elements
+    scalar = struct.pack('<BBBB', 2, 0, 0, 0)                # dataspace v2, scalar
+    # attribute v3: name 'gain' (UTF-8), float64 scalar
+    attr = struct.pack('<BBHHHB', 3, 0, 5, len(f64), len(scalar), 1) + b'gain\x00' + f64 + scalar + struct.pack('<d', 2.5)
+    # dataset A: compact layout (v3), int16[5]
+    vals = np.array([3, -1, 4, -1, 5], dtype='<i2')
+    compact = struct.pack('<BBH', 3, 0, vals.nbytes) + vals.tobytes()
+    ds_a = put(ohdr([msg(0x01, space1), msg(0x03, i16), msg(0x08, compact), msg(0x0C, attr)]))
+    # dataset B: layout v4, single chunk, deflate, float64[5]; second half of its messages in a continuation block
+    data = np.linspace(0, 1, 5)
+    comp = zlib.compress(data.tobytes(), 4)
+    chunk = put(comp)
+    filt = struct.pack('<BBHHHI', 2, 1, 1, 1, 1, 4)          # pipeline v2: deflate, flags 1, one client value
+    lay4 = struct.pack('<BBBBB', 4, 2, 0x02, 2, 1) + bytes([5, 8]) + bytes([1]) + struct.pack('<QI', len(comp), 0) + \
+        struct.pack('<Q', chunk)
+    cont_body = msg(0x0B, filt, True) + msg(0x08, lay4, True)
+    cont = put(b'OCHK' + cont_body + b'\x00' * 4)
+    ds_b = put(ohdr([msg(0x01, space1, True), msg(0x03, f64, True),
+                     msg(0x10, struct.pack('<QQ', cont, len(cont_body) + 8), True)], flags=0x04 | 0x20))
+    # a sub-group holding B, and the root group holding A and the sub-group: link messages with 1-byte name length
+    def link(name, addr):
+        return struct.pack('<BB', 1, 0) + bytes([len(name)]) + name + struct.pack('<Q', addr)
+    linfo = struct.pack('<BBQQ', 0, 0, hdf5_min.UNDEF, hdf5_min.UNDEF)
+    sub = put(ohdr([msg(0x02, linfo), msg(0x06, link(b'B', ds_b))]))
+    root = put(ohdr([msg(0x02, linfo), msg(0x06, link(b'A', ds_a)), msg(0x06, link(b'sub', sub))], flags=1))
+    buf[0:48] = hdf5_min.SIGNATURE + struct.pack('<BBBBQQQQI', 2, 8, 8, 0, 0, hdf5_min.UNDEF, len(buf), root, 0)
+    tree, lossy = hdf5_min.load_tree(bytes(buf))
+    assert lossy == [] and sorted(tree.keys()) == ['A', 'sub']
+    assert tree['A'].dtype == np.dtype('<i2') and np.array_equal(tree['A'][()], vals)
+    assert tree['A'].attrs['gain'] == 2.5
+    assert np.array_equal(tree['sub/B'][()], data) and tree['sub/B'].compression == 'gzip'
+    # and what was read can be written back in the conservative format and read again
+    again, _ = hdf5_min.load_tree(hdf5_min.dump_tree(tree))
+    check_structure(hdf5_min.dump_tree(tree))
+    assert np.array_equal(again['A'][()], vals) and np.array_equal(again['sub/B'][()], data)
+    assert again['A'].attrs['gain'] == 2.5
