@@ -14,7 +14,10 @@
 
 namespace nrq {
 
-constexpr int kNormThreads = 256;
+#ifndef NRQ_NORM_THREADS
+#define NRQ_NORM_THREADS 256
+#endif
+constexpr int kNormThreads = NRQ_NORM_THREADS;
 #ifndef NRQ_NORM_WIN
 #define NRQ_NORM_WIN 2048
 #endif
