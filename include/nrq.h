@@ -198,6 +198,14 @@ typedef struct nrq_handle nrq_handle;
 nrq_handle* nrq_create(int32_t device);
 void nrq_destroy(nrq_handle* h);
 int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_params* p, const nrq_results* out);
+/* The same call in two halves, so that a host that keeps reads coming (the re-squiggle worker's loop,
+ * resquiggle.py:410-440) never lets the copy / kernel pipeline drain between batches: _submit queues the whole
+ * batch and returns a ticket (>= 0; negative = error as above), _wait blocks until that batch's results are in the
+ * caller's host arrays.  Batches complete in submission order.  The host buffers of a submitted batch must stay
+ * valid and untouched until its ticket has been waited for; at most 16 tickets may be outstanding. */
+int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, const nrq_params* p,
+                                         const nrq_results* out);
+int nrq_resquiggle_batch_host_wait(nrq_handle* h, int64_t ticket);
 /* number of kernel launches the library has issued on this process (all entry points) */
 int64_t nrq_launch_count(void);
 

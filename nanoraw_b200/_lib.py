@@ -63,6 +63,9 @@ SYMBOLS = {
     'nrq_destroy': (None, [_P]),
     'nrq_resquiggle_batch_host': (C.c_int, [_P, C.POINTER(NrqBatch), C.POINTER(NrqParams),
                                             C.POINTER(NrqResults)]),
+    'nrq_resquiggle_batch_host_submit': (C.c_int64, [_P, C.POINTER(NrqBatch), C.POINTER(NrqParams),
+                                                     C.POINTER(NrqResults)]),
+    'nrq_resquiggle_batch_host_wait': (C.c_int, [_P, C.c_int64]),
     'nrq_launch_count': (C.c_int64, []),
 }
 

@@ -347,11 +347,16 @@ struct nrq_slot {
   size_t off_stage_elems = 0;
 };
 
+constexpr int kTickets = 16;  // completion events of the most recent submissions
+
 struct nrq_handle {
   int device;
   int n_slots = kSlotsDefault;
   cudaStream_t h2d = nullptr, d2h = nullptr;
   nrq_slot slots[kMaxSlots];
+  cudaEvent_t ticket[kTickets] = {};
+  int64_t next_ticket = 0;
+  int64_t chunk_index = 0;  // slots are taken round-robin across calls, so a new call queues behind the last one
 };
 
 static void* dev_buf(nrq_slot& sl, size_t idx, size_t bytes, cudaError_t* err) {
@@ -400,20 +405,29 @@ void nrq_destroy(nrq_handle* h) {
     for (cudaEvent_t e : {sl.up_done, sl.k_done, sl.done}) if (e) cudaEventDestroy(e);
     if (sl.stream) cudaStreamDestroy(sl.stream);
   }
+  for (cudaEvent_t e : h->ticket) if (e) cudaEventDestroy(e);
   if (h->h2d) cudaStreamDestroy(h->h2d);
   if (h->d2h) cudaStreamDestroy(h->d2h);
   delete h;
 }
 
-int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_params* p, const nrq_results* out) {
+int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, const nrq_params* p,
+                                         const nrq_results* out) {
   if (!h) return fail("handle is NULL");
   if (int e = check_batch(b)) return e;
   if (int e = check_params(p)) return e;
   if (!out) return fail("results is NULL");
   const int R = b->n_reads;
-  if (R == 0) return 0;
   cudaError_t ce = cudaSetDevice(h->device);
   if (ce != cudaSuccess) return fail("cudaSetDevice", ce);
+  const int64_t id = h->next_ticket++;
+  cudaEvent_t& done_ev = h->ticket[id % kTickets];
+  if (!done_ev && cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming) != cudaSuccess)
+    return fail("nrq_resquiggle_batch_host_submit: event creation failed");
+  if (R == 0) {
+    cudaEventRecord(done_ev, h->d2h);
+    return id;
+  }
   cudaError_t err = cudaSuccess;
   int rc = 0;
 
@@ -423,7 +437,7 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     long long v = atoll(env);
     if (v > 0) kChunkBytes = v;
   }
-  int chunk_index = 0;
+  int64_t& chunk_index = h->chunk_index;
   for (int lo = 0; lo < R && rc == 0 && err == cudaSuccess; ++chunk_index) {
     // ---- next chunk: reads [lo, hi) holding about kChunkBytes of input
     int hi = lo;
@@ -525,13 +539,32 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
     cudaEventRecord(sl.done, h->d2h);
     lo = hi;
   }
-  for (int i = -2; i < h->n_slots; ++i) {
-    cudaError_t e = cudaStreamSynchronize(i == -2 ? h->h2d : i == -1 ? h->d2h : h->slots[i].stream);
-    if (e != cudaSuccess && err == cudaSuccess) err = e;
+  if (rc || err != cudaSuccess) {  // leave nothing of a failed submission in flight
+    for (int i = -2; i < h->n_slots; ++i)
+      cudaStreamSynchronize(i == -2 ? h->h2d : i == -1 ? h->d2h : h->slots[i].stream);
+    if (rc) return rc;
+    return fail("nrq_resquiggle_batch_host", err);
   }
-  if (rc) return rc;
-  if (err != cudaSuccess) return fail("nrq_resquiggle_batch_host", err);
+  // every download of this batch is queued on the one device->host stream: its end marks the batch's end
+  ce = cudaEventRecord(done_ev, h->d2h);
+  if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_host_submit: event record", ce);
+  return id;
+}
+
+int nrq_resquiggle_batch_host_wait(nrq_handle* h, int64_t ticket) {
+  if (!h) return fail("handle is NULL");
+  if (ticket < 0 || ticket >= h->next_ticket) return fail("nrq_resquiggle_batch_host_wait: unknown ticket");
+  if (h->next_ticket - ticket > kTickets) return 0;  // its event has been reused by a later batch, which queued behind it and is waited for by its own ticket
+  cudaError_t ce = cudaSetDevice(h->device);
+  if (ce == cudaSuccess) ce = cudaEventSynchronize(h->ticket[ticket % kTickets]);
+  if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_host_wait", ce);
   return 0;
+}
+
+int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_params* p, const nrq_results* out) {
+  const int64_t ticket = nrq_resquiggle_batch_host_submit(h, b, p, out);
+  if (ticket < 0) return (int)ticket;
+  return nrq_resquiggle_batch_host_wait(h, ticket);
 }
 
 }  // extern "C"

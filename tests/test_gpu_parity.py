@@ -324,6 +324,54 @@ def test_host_buffer_entry_point(engine, chunk_bytes, monkeypatch):
 
 
 
+def test_host_entry_point_submit_and_wait(engine, monkeypatch):
+    """three batches queued back to back through nrq_resquiggle_batch_host_submit, waited for in order and out of
+    order, give what the synchronous call gives for each"""
+    import ctypes as C
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.engine import ResquiggleParams
+    monkeypatch.setenv('NRQ_HOST_CHUNK_BYTES', '200000')  # several chunks per batch, slots shared across batches
+    lib = _lib.load()
+    params = ResquiggleParams()
+    pc = params.to_c()
+    genome = synth.make_genome(200_000, seed=9)
+    h = lib.nrq_create(engine.device.index or 0)
+    assert h
+    jobs = []
+    for k, n in enumerate((7, 12, 5)):
+        reads = synth.make_reads(n, synth.config_short(49000 + 100 * k), genome=genome)
+        batch = ReadBatch.from_reads(reads)
+        R, A = batch.n_reads, batch.total_align
+        hb = _lib.NrqBatch()
+        hb.n_reads = R
+        keep = [np.ascontiguousarray(getattr(batch, f)) for f in ReadBatch.FIELDS]
+        for f, arr in zip(ReadBatch.FIELDS, keep):
+            setattr(hb, f, arr.ctypes.data)
+        outs = {'status': np.full(R, -1, np.int32), 'n_bases': np.zeros(R, np.int32), 'n_indels': np.zeros(R, np.int32),
+                'scale_values': np.zeros(4 * R), 'new_segs': np.zeros(A + R, np.int32), 'norm_mean': np.zeros(A),
+                'norm_stdev': np.zeros(A), 'ev_start': np.zeros(A, np.uint32), 'ev_length': np.zeros(A, np.uint32),
+                'ev_base': np.zeros(A, np.uint8), 'region_samples': np.zeros(R, np.int32)}
+        hr = _lib.NrqResults()
+        for name, v in outs.items():
+            setattr(hr, name, v.ctypes.data)
+        ticket = lib.nrq_resquiggle_batch_host_submit(h, C.byref(hb), C.byref(pc), C.byref(hr))
+        assert ticket == k
+        jobs.append((batch, keep, hb, hr, outs, ticket))
+    assert lib.nrq_resquiggle_batch_host_wait(h, 99) != 0          # unknown ticket
+    for idx in (1, 0, 2):                                           # batches complete in submission order
+        _lib.check(lib.nrq_resquiggle_batch_host_wait(h, jobs[idx][5]), 'wait')
+    _lib.check(lib.nrq_resquiggle_batch_host_wait(h, 0), 'wait twice')
+    lib.nrq_destroy(h)
+    for batch, _, _, _, outs, _ in jobs:
+        want = engine.run(batch, params)
+        assert np.array_equal(outs['status'], want.status) and np.array_equal(outs['n_bases'], want.n_bases)
+        for r in range(batch.n_reads):
+            o, n = int(batch.align_off[r]), int(want.n_bases[r])
+            assert np.array_equal(outs['new_segs'][o + r:o + r + n + 1], want.new_segs_of(r))
+            assert np.array_equal(outs['norm_mean'][o:o + n], want.norm_mean[o:o + n])
+            assert np.array_equal(outs['ev_length'][o:o + n], want.ev_length[o:o + n])
+
+
 def test_host_path_equals_torch_path_and_pinned_batcher(engine):
     """engine.run (C-ABI host entry point) == the torch-tensor route == a PinnedBatcher fed read by read"""
     from nanoraw_b200.batch import PinnedBatcher
