@@ -576,12 +576,11 @@ def fast5_leg(args, reads):
 
         def one_pass():
             pend = pending_reads()
+            pipe = rsq.BatchPipeline('median', 5, None, None, 'Basecall_1D_000', 'RawGenomeCorrected_000', True, None)
             failed = []
-            for lo in range(0, len(pend), rsq.DEVICE_BATCH_READS):
-                failed += rsq.resquiggle_reads_batch(
-                    pend[lo:lo + rsq.DEVICE_BATCH_READS], 'median', 5, None, None, 'Basecall_1D_000',
-                    'RawGenomeCorrected_000', True, None)
-            return failed
+            for lo in range(0, len(pend), rsq.DEVICE_BATCH_READS):  # as resquiggle_worker feeds its batches
+                failed += pipe.feed(pend[lo:lo + rsq.DEVICE_BATCH_READS])
+            return failed + pipe.drain()
 
         one_pass()                                   # warm-up: pool start-up, pinned staging, kernels
         fast5_jobs.map_jobs(synth.drop_corrected_job, jobs)      # back to the state prep_fast5 leaves (not timed)
@@ -598,7 +597,7 @@ def fast5_leg(args, reads):
                 'failed_reads': len(failed), 'seconds': dt, 'io_procs': fast5_jobs.io_procs(),
                 'bytes_per_file_in': int(np.mean(sizes)), 'events_rows_file0': int(len(ev)),
                 'setup_seconds': setup_s,
-                'what': 'resquiggle_reads_batch: FAST5 open + raw signal read, device batch, RawGenomeCorrected '
+                'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal read, device batch, RawGenomeCorrected '
                         'write-back into the same file (hdf5_min.py, gzip level 4); mapper and basecall '
                         'event parsing not included'}
     finally:
@@ -630,7 +629,7 @@ def main():
     ap.add_argument('--cpu-reads', type=int, default=None)
     ap.add_argument('--ref-reads', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--fast5-files', type=int, default=1024,
+    ap.add_argument('--fast5-files', type=int, default=2048,
                     help='FAST5 files on disk for the e2e_fast5 leg (N = 1 only; 0 = skip)')
     args = ap.parse_args()
     claim_stdout()

@@ -4,7 +4,9 @@ The reference opens each FAST5 file inside its re-squiggle worker, one read at a
 (resquiggle.py:328-347 read, :80-135 write).  Here a GPU worker handles hundreds of reads per
 device batch (about 10 ms of kernels), so the file work of a batch -- HDF5 parsing, inflate of the
 raw signal, deflate of the new event table, about 12 ms per read -- is what bounds the worker; it
-runs on a small pool of I/O processes.  Nothing GPU-related is imported in those processes.
+runs on a pool of I/O processes, and resquiggle.BatchPipeline keeps that pool busy: the reads of the
+next batch are queued before the current batch goes through the device.  Nothing GPU-related is
+imported in those processes.
 
 NRQ_IO_PROCS sets the pool size (default: the host cores, at most 32; 0 or 1 = do the work inline).
 One file is only ever handled by one job at a time (the one-writer-per-file rule, :422-424):
@@ -68,6 +70,16 @@ def write_job(args):
         return None
     except Exception as e:  # noqa: BLE001
         return str(e)
+
+
+def start_jobs(fn, jobs):
+    """submit fn over jobs and return at once: an iterable of the results, in order, that blocks as it is read"""
+    p = pool()
+    if not jobs:
+        return []
+    if p is None or any(str(j[0]).startswith('mem://') for j in jobs):
+        return [fn(j) for j in jobs]
+    return p.map(fn, jobs, chunksize=max(1, len(jobs) // (4 * io_procs()) or 1))
 
 
 def map_jobs(fn, jobs):

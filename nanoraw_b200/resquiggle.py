@@ -192,69 +192,130 @@ class _PendingRead(object):
         self.rows = _rows(self.alignVals)
 
 
+class BatchPipeline(object):
+    """The batched body of resquiggle_read (resquiggle.py:318-401) as a three-deep pipeline over device batches:
+    while the FAST5 reads of batch n + 1 run on the I/O processes, batch n goes through the device and its
+    RawGenomeCorrected write-backs are queued behind them, and batch n - 1's write-backs are being collected.
+    `feed(pending)` takes the next list of _PendingRead and returns the failures [(error string, read)] that have
+    become known; `drain()` finishes what is in flight.  A file is never handled by two jobs at once (the
+    one-writer-per-file rule, :422-424): a batch that shares a file with unfinished work waits for it."""
+
+    def __init__(self, norm_type, outlier_thresh, timeout, num_cpts_limit, basecall_group, corrected_group,
+                 compute_sd, pore_model, min_event_obs=4, in_place=True, engine=None):
+        self.norm_type, self.outlier_thresh = norm_type, outlier_thresh
+        self.timeout, self.num_cpts_limit = timeout, num_cpts_limit
+        self.basecall_group, self.corrected_group = basecall_group, corrected_group
+        self.compute_sd, self.pore_model = compute_sd, pore_model
+        self.min_event_obs, self.in_place, self.engine = min_event_obs, in_place, engine
+        self._reading = None   # (pending, iterator over read results)
+        self._writing = []     # [(reads being written, iterator over write results, file names)]
+
+    # ---- stage 1: FAST5 reads of a batch, on the I/O processes
+    def _start_reads(self, pending):
+        from . import fast5_jobs
+        jobs = [(pr.fast5_fn, self.norm_type, self.basecall_group, pr.read_info.Subgroup) for pr in pending]
+        return pending, fast5_jobs.start_jobs(fast5_jobs.read_job, jobs)
+
+    # ---- stage 2: one device batch (a1..a7), then the write-backs are queued
+    def _process(self, pending, loaded):
+        from . import fast5_jobs
+        from .engine import ResquiggleParams, get_engine
+        norm_type = self.norm_type
+        failed, ready = [], []
+        for pr, got in zip(pending, loaded):
+            try:
+                if got[0] != 'ok':
+                    raise NotImplementedError(got[1])
+                chan, raw, ev_means, ev_kmers = got[1:]
+                pr.raw = np.ascontiguousarray(raw, dtype=np.int16)
+                pr.given = nh.given_shift_scale(norm_type, chan, self.pore_model, ev_means, ev_kmers)
+                ready.append(pr)
+            except Exception as e:  # noqa: BLE001 -- mirrors the worker's blanket except (:434)
+                failed.append((str(e), pr))
+        if not ready:
+            return failed
+        engine = self.engine or get_engine()
+        batcher = _batcher()
+        batcher.reset()
+        for pr in ready:  # straight into pinned CSR staging: no intermediate copies
+            batcher.add(pr.raw, int(pr.read_start), pr.starts, pr.rows[0].encode(), pr.rows[1].encode(),
+                        None if norm_type == 'median' else (float(pr.given[0]), float(pr.given[1])))
+        params = ResquiggleParams(
+            norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=self.outlier_thresh,
+            compute_sd=self.compute_sd, num_cpts_limit=self.num_cpts_limit, timeout=self.timeout,
+            min_event_obs=self.min_event_obs)
+        res = engine.run_host(batcher, params)
+        writes, writers = [], []
+        for r, pr in enumerate(ready):
+            pr.raw = None
+            exc = exception_for(res.status[r])
+            if exc is not None:
+                failed.append((str(exc), pr))
+                continue
+            if not self.in_place:
+                continue
+            try:
+                sv = res.scale_values_of(r)
+                if norm_type != 'median':
+                    sv = (pr.given[0], pr.given[1], sv[2], sv[3])
+                events = res.events_of(r)
+                writes.append((
+                    pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, res.new_segs_of(r),
+                    events['base'].tobytes().decode(), pr.rows, pr.starts, None,
+                    nh.scaleValues(*sv), self.corrected_group, pr.read_info.Subgroup, norm_type,
+                    self.outlier_thresh, self.compute_sd, events))
+                writers.append(pr)
+            except Exception as e:  # noqa: BLE001
+                failed.append((str(e), pr))
+        if writes:
+            self._writing.append((writers, fast5_jobs.start_jobs(fast5_jobs.write_job, writes),
+                                  set(pr.fast5_fn for pr in writers)))
+        return failed
+
+    # ---- stage 3: results of the write-backs
+    def _collect_writes(self, keep=0):
+        failed = []
+        while len(self._writing) > keep:
+            writers, results, _ = self._writing.pop(0)
+            failed += [(err, pr) for pr, err in zip(writers, results) if err is not None]
+        return failed
+
+    def _advance(self):
+        """push the batch whose reads are in flight through the device"""
+        failed = []
+        if self._reading is not None:
+            pending, loaded = self._reading
+            self._reading = None
+            failed += self._process(pending, list(loaded))
+        return failed
+
+    def feed(self, pending):
+        failed = []
+        files = set(pr.fast5_fn for pr in pending)
+        busy = set(pr.fast5_fn for pr in self._reading[0]) if self._reading else set()
+        for _, _, names in self._writing:
+            busy |= names
+        if files & busy:  # (only with several subgroups per file)
+            failed += self.drain()
+        nxt = self._start_reads(pending)      # queued behind the write-backs already in flight
+        failed += self._advance()             # the previous batch: device, then its write-backs are queued
+        failed += self._collect_writes(keep=1)
+        self._reading = nxt
+        return failed
+
+    def drain(self):
+        return self._advance() + self._collect_writes()
+
+
 def resquiggle_reads_batch(
         pending, norm_type, outlier_thresh, timeout, num_cpts_limit,
         basecall_group, corrected_group, compute_sd, pore_model,
         min_event_obs=4, in_place=True, engine=None):
-    """The batched body of resquiggle_read (resquiggle.py:318-401) for a list of _PendingRead:
-    FAST5 read -> one device batch (a1..a7) -> FAST5 write.  Returns [(error string, read)] for
-    the reads that failed, with the reference's messages."""
-    from .engine import ResquiggleParams, get_engine
-    from . import fast5_jobs
-    failed = []
-    ready = []
-    # FAST5 reads of the whole batch, on the I/O processes
-    loaded = fast5_jobs.map_jobs(fast5_jobs.read_job, [
-        (pr.fast5_fn, norm_type, basecall_group, pr.read_info.Subgroup) for pr in pending])
-    for pr, got in zip(pending, loaded):
-        try:
-            if got[0] != 'ok':
-                raise NotImplementedError(got[1])
-            chan, raw, ev_means, ev_kmers = got[1:]
-            pr.raw = np.ascontiguousarray(raw, dtype=np.int16)
-            pr.given = nh.given_shift_scale(norm_type, chan, pore_model, ev_means, ev_kmers)
-            ready.append(pr)
-        except Exception as e:  # noqa: BLE001 -- mirrors the worker's blanket except (:434)
-            failed.append((str(e), pr))
-    if not ready:
-        return failed
-    engine = engine or get_engine()
-    batcher = _batcher()
-    batcher.reset()
-    for pr in ready:  # straight into pinned CSR staging: no intermediate copies
-        batcher.add(pr.raw, int(pr.read_start), pr.starts, pr.rows[0].encode(), pr.rows[1].encode(),
-                    None if norm_type == 'median' else (float(pr.given[0]), float(pr.given[1])))
-    params = ResquiggleParams(
-        norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=outlier_thresh,
-        compute_sd=compute_sd, num_cpts_limit=num_cpts_limit, timeout=timeout,
-        min_event_obs=min_event_obs)
-    res = engine.run_host(batcher, params)
-    writes, writers = [], []
-    for r, pr in enumerate(ready):
-        exc = exception_for(res.status[r])
-        if exc is not None:
-            failed.append((str(exc), pr))
-            continue
-        if not in_place:
-            continue
-        try:
-            sv = res.scale_values_of(r)
-            if norm_type != 'median':
-                sv = (pr.given[0], pr.given[1], sv[2], sv[3])
-            events = res.events_of(r)
-            writes.append((
-                pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, res.new_segs_of(r),
-                events['base'].tobytes().decode(), pr.rows, pr.starts, None,
-                nh.scaleValues(*sv), corrected_group, pr.read_info.Subgroup, norm_type,
-                outlier_thresh, compute_sd, events))
-            writers.append(pr)
-        except Exception as e:  # noqa: BLE001
-            failed.append((str(e), pr))
-    # RawGenomeCorrected write-back of the whole batch, on the I/O processes
-    for pr, err in zip(writers, fast5_jobs.map_jobs(fast5_jobs.write_job, writes)):
-        if err is not None:
-            failed.append((err, pr))
-    return failed
+    """One device batch, start to finish: FAST5 read -> device (a1..a7) -> FAST5 write for a list of
+    _PendingRead.  Returns [(error string, read)] for the reads that failed, with the reference's messages."""
+    pipe = BatchPipeline(norm_type, outlier_thresh, timeout, num_cpts_limit, basecall_group, corrected_group,
+                         compute_sd, pore_model, min_event_obs, in_place, engine)
+    return pipe.feed(pending) + pipe.drain()
 
 
 def resquiggle_read(
@@ -295,7 +356,10 @@ def resquiggle_worker(
     twice (the reference's one-writer-per-file rule, :422-424)."""
     num_processed = 0
     done = False
+    pending = []
     carry = []  # later subgroups of files already seen, for following batches
+    pipe = BatchPipeline(norm_type, outlier_thresh, timeout, num_cpts_limit, basecall_group, corrected_group,
+                         compute_sd, pore_model)
     while not done or carry:
         pending, carry_next = [], []
         seen_files = set()
@@ -324,13 +388,17 @@ def resquiggle_worker(
         if not pending:
             continue
         try:
-            failed = resquiggle_reads_batch(
-                pending, norm_type, outlier_thresh, timeout, num_cpts_limit,
-                basecall_group, corrected_group, compute_sd, pore_model)
+            failed = pipe.feed(pending)
         except Exception as e:  # noqa: BLE001 -- infrastructure failure: every read of the batch fails
             failed = [(str(e), pr) for pr in pending]
         for text, pr in failed:
             failed_reads_q.put((text, pr.read_info.Subgroup + ' :: ' + pr.fast5_fn))
+    try:
+        failed = pipe.drain()
+    except Exception as e:  # noqa: BLE001
+        failed = [(str(e), pr) for pr in pending]
+    for text, pr in failed:
+        failed_reads_q.put((text, pr.read_info.Subgroup + ' :: ' + pr.fast5_fn))
     return
 
 
