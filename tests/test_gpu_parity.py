@@ -258,6 +258,51 @@ def test_groups_larger_than_the_planning_window(engine):
         assert close(res.events_of(r)['norm_mean'], out['events']['norm_mean'])
 
 
+def test_random_generator_settings_against_oracle(engine):
+    """24 random settings of the read generator (indel rates from none to one base in three, dwell 6 to 24 samples,
+    quantised to noisy signals, spike rates up to 2 %, narrow and wide DAC ranges), 6 reads each, whole path against
+    the oracle: statuses, boundaries bit-exact, statistics inside the contract"""
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.engine import ResquiggleParams
+    rng = np.random.default_rng(20260101)
+    genome = synth.make_genome(400_000, seed=5)
+    reads = []
+    for k in range(24):
+        cfg = synth.SynthConfig(
+            span_mean=float(rng.integers(300, 1800)), span_sd=50.0,
+            del_rate=float(rng.choice([0.0, 0.02, 0.06, 0.12, 0.18])),
+            ins_rate=float(rng.choice([0.0, 0.02, 0.06, 0.12, 0.18])),
+            mismatch_rate=float(rng.uniform(0.0, 0.15)), indel_len_p=float(rng.uniform(0.4, 0.95)),
+            dwell_mean=float(rng.uniform(6.0, 24.0)), dwell_min=int(rng.integers(1, 4)),
+            level_sd=float(rng.choice([3.0, 25.0, 60.0, 400.0, 1500.0])),
+            noise_sd=float(rng.choice([0.0, 0.7, 5.0, 12.0, 60.0])),
+            spike_rate=float(rng.choice([0.0, 5e-4, 5e-3, 2e-2])), spike_sd=float(rng.choice([50.0, 400.0, 4000.0])),
+            clip_bases=(0, int(rng.integers(0, 40))), seed_base=90000 + 100 * k)
+        reads += synth.make_reads(6, cfg, genome=genome)
+    res = engine.run(ReadBatch.from_reads(reads), ResquiggleParams())
+    n_ok = 0
+    for r, read in enumerate(reads):
+        try:
+            out = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
+                                      read.read_align.decode(), read.genome_align.decode())
+        except orc.RegionUnsatisfiable:
+            assert res.status[r] == _lib.ST_UNSATISFIABLE, r
+            continue
+        except Exception as e:  # the reference's own failures, by message
+            assert not res.ok(r) and res.error(r) == str(e), (r, res.error(r), str(e))
+            continue
+        assert res.ok(r), (r, res.error(r))
+        n_ok += 1
+        assert res.scale_values_of(r) == tuple(float(v) for v in out['scale_values']), r
+        assert np.array_equal(res.new_segs_of(r), out['new_segs']), r
+        ev = res.events_of(r)
+        for col in ('start', 'length', 'base'):
+            assert np.array_equal(ev[col], out['events'][col]), (r, col)
+        assert close(ev['norm_mean'], out['events']['norm_mean']), r
+        assert close(ev['norm_stdev'], out['events']['norm_stdev']), r
+    assert n_ok >= len(reads) // 2
+
+
 def test_unsatisfiable_region_terminates(engine):
     """mean dwell <= 5 samples/base: the reference loops forever (resquiggle.py:210-215);
     the device path must stop with NRQ_ST_UNSATISFIABLE like the oracle's guard."""
