@@ -373,30 +373,31 @@ __device__ __forceinline__ void push_group(SegCtx& c, int start, int stop, int l
 
 // The driver loop of get_indel_groups (:286-314), indel by indel, from a group (lo .. hi, maxend) that is still
 // open and indel k as the next one to look at, until that group has been finished and pushed.  On return k is the
-// first indel of the next group (n_ind when the read's last group was pushed).
-__device__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend) {
+// first indel of the next group (n_ind when the read's last group was pushed).  One call site of close_group and
+// one of this function: every inlined copy carries the whole change-point search with it.
+__device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend) {
   int start, stop;
-  for (; k < c.n_ind; ++k) {
-    const int4 nxt = c.ind[k];
-    if (maxend >= nxt.x) {  // :291-292
-      hi = k;
-      maxend = max(maxend, nxt.y);
-      continue;
+  for (;;) {
+    const bool more = k < c.n_ind;
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if (more) {
+      nxt = c.ind[k];
+      if (maxend >= nxt.x) {  // :291-292
+        hi = k++;
+        maxend = max(maxend, nxt.y);
+        continue;
+      }
     }
-    int st = close_group(c, lo, hi, maxend, start, stop);
+    int st = close_group(c, lo, hi, maxend, start, stop);  // :293-294, and :307-314 for the read's last group
     if (st != NRQ_ST_OK) return st;
-    if (stop >= nxt.x) {  // :299-300
-      hi = k;
+    if (more && stop >= nxt.x) {  // :299-300
+      hi = k++;
       maxend = max(maxend, nxt.y);
       continue;
     }
     push_group(c, start, stop, lo, maxend);  // :302-304
     return NRQ_ST_OK;
   }
-  int st = close_group(c, lo, hi, maxend, start, stop);  // :307-314
-  if (st != NRQ_ST_OK) return st;
-  push_group(c, start, stop, lo, maxend);
-  return NRQ_ST_OK;
 }
 
 constexpr int kPlanGeneric = 15;       // record status: take the indel-by-indel path for this group
@@ -452,15 +453,11 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     }
     unsigned todo = __ballot_sync(kFull, planned);
     __syncwarp();
-    if (todo == 0u) {  // more than 32 indels in one group
-      int kk = k + 1;
-      int st = drive_until_push(c, kk, k, k, c.ind[k].y);
-      if (st != NRQ_ST_OK) return st;
-      k = kk;
-      continue;
-    }
-    // ---- walk the planned groups
+    // ---- walk the planned groups; whatever cannot be taken from a plan goes indel by indel (one call site below)
     int next_k = k;
+    bool drive = todo == 0u;  // more than 32 indels in one group
+    int d_lo = k, d_hi = k, d_maxend = 0, d_k = k + 1;
+    if (drive) d_maxend = c.ind[k].y;
     while (todo) {
       const int s = __ffs(todo) - 1;
       todo &= todo - 1;
@@ -469,25 +466,29 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       const int hi = lo + ((rec.z >> kPlanKBits) & 31);
       int st = (rec.z >> (kPlanKBits + 5)) & 15;
       int start = rec.x, stop = rec.y, maxend = rec.w;
-      if (st == kPlanGeneric) {
-        st = close_group(c, lo, hi, maxend, start, stop);
-      } else {
-        if (st != NRQ_ST_OK) return st;
-        st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop]);
+      if (st == kPlanGeneric) {  // a plan that did not fit its record: same group, from scratch
+        drive = true;
+        d_lo = lo; d_hi = hi; d_maxend = maxend; d_k = hi + 1;
+        break;
       }
+      if (st != NRQ_ST_OK) return st;
+      st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop]);
       if (st != NRQ_ST_OK) return st;
       if (hi + 1 < c.n_ind) {
         const int4 nxt = c.ind[hi + 1];
         if (stop >= nxt.x) {  // :299-300: the finished group reaches the next indel and stays open
-          int kk = hi + 2;
-          st = drive_until_push(c, kk, lo, hi + 1, max(maxend, nxt.y));
-          if (st != NRQ_ST_OK) return st;
-          next_k = kk;
-          break;  // plans made behind this point may no longer hold
+          drive = true;       // plans made behind this point may no longer hold
+          d_lo = lo; d_hi = hi + 1; d_maxend = max(maxend, nxt.y); d_k = hi + 2;
+          break;
         }
       }
       push_group(c, start, stop, lo, maxend);
       next_k = hi + 1;
+    }
+    if (drive) {
+      int st = drive_until_push(c, d_k, d_lo, d_hi, d_maxend);
+      if (st != NRQ_ST_OK) return st;
+      next_k = d_k;
     }
     k = next_k;
   }
