@@ -202,7 +202,8 @@ int nrq_resquiggle_batch_host(nrq_handle* h, const nrq_batch* b, const nrq_param
  * resquiggle.py:410-440) never lets the copy / kernel pipeline drain between batches: _submit queues the whole
  * batch and returns a ticket (>= 0; negative = error as above), _wait blocks until that batch's results are in the
  * caller's host arrays.  Batches complete in submission order.  The host buffers of a submitted batch must stay
- * valid and untouched until its ticket has been waited for; at most 16 tickets may be outstanding. */
+ * valid and untouched until its ticket has been waited for; at most 16 tickets may be outstanding.  A handle is
+ * used from one host thread at a time (one handle per worker; handles are independent of each other). */
 int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, const nrq_params* p,
                                          const nrq_results* out);
 int nrq_resquiggle_batch_host_wait(nrq_handle* h, int64_t ticket);
