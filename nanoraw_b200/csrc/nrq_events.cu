@@ -481,6 +481,58 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         // sums carried in from earlier steps for the base that ends at the first boundary of this round
         const long long c1 = run1 - prev1;
         const unsigned long long c2 = run2 - prev2;
+        // ---- round of a step with clipped samples (one step in eight): bases 1 .. nb - 2 only, carried sums fit 32
+        // bits; the clipped samples of each base are differences of the packed (below, above) counter prefixes, and
+        // only a base that holds one takes the general statistics
+        if (anyc && cur >= 2 && cur + 32 < nb && (c2 >> 30) == 0ull) {
+          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][(sl & 7) >> 2][t][sl & 3];
+          const unsigned pEC = __shfl_up_sync(0xffffffffu, EC, 1);
+          int nl = (int)(EC & 0xffffu), nh = (int)(EC >> 16);
+          if (lane == 0) {  // the base may have begun in an earlier step
+            pE1 = -(int)c1; pE2 = 0u - (unsigned)c2; bpos = prevpos;
+            nl += runl - prevl;
+            nh += runh - prevh;
+          } else {
+            nl -= (int)(pEC & 0xffffu);
+            nh -= (int)(pEC >> 16);
+          }
+          if (inb) {
+            const int n = pos - bpos;
+            const int S1 = E1 - pE1;
+            const unsigned S2 = E2 - pE2;
+            double mean = qnan, sd = qnan;
+            if (n > 0) {
+              if ((nl | nh) == 0) {
+                const double dn = (double)n;
+                const double rn = (unsigned)n < 64u ? rcp_tab[n] : ev_rcp(dn);
+                const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
+                mean = sum_u * rn;
+                if (R.compute_sd) {
+                  const unsigned long long num = (unsigned long long)(unsigned)n * (unsigned long long)S2 -
+                                                 (unsigned long long)((long long)S1 * (long long)S1);
+                  sd = ev_sqrt((double)num * rn * R.inv_scale2 * rn);
+                }
+              } else {
+                ev_base_stats(R, n, (long long)S1, (unsigned long long)S2, nl, nh, mean, sd);
+              }
+            }
+            const unsigned o = (unsigned)(cur + lane - 1);
+            o_mean[o] = mean;
+            o_sd[o] = sd;
+            o_start[o] = (uint32_t)bpos;
+            o_length[o] = (uint32_t)n;
+          }
+          const unsigned last = __shfl_sync(0xffffffffu, EC, cntb - 1);
+          prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
+          prev2 = run2 + __shfl_sync(0xffffffffu, E2, cntb - 1);
+          prevl = runl + (int)(last & 0xffffu);
+          prevh = runh + (int)(last >> 16);
+          prevpos = __shfl_sync(0xffffffffu, pos, cntb - 1);
+          cur += cntb;
+          pos = load_pos(cur);
+          if (cntb < 32) break;
+          continue;
+        }
         // ---- common round: no clipped sample in play, bases 1 .. nb - 2 only, carried sums fit 32 bits
         if (!anyc && cur >= 2 && cur + 32 < nb && (c2 >> 30) == 0ull && runl == prevl && runh == prevh) {
           if (lane == 0) { pE1 = -(int)c1; pE2 = 0u - (unsigned)c2; bpos = prevpos; }
