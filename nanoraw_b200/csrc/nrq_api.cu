@@ -338,6 +338,7 @@ constexpr int kSlotsDefault = 6;  // NRQ_HOST_SLOTS overrides (1..kMaxSlots), re
 // the other), so slots x chunk >= ~300 MB must be in flight to keep both PCIe directions busy, while a small
 // call still wants several chunks to overlap at all.  Measured sweep in profiles/README.md.
 constexpr int64_t kChunkBytesMin = 32ll << 20, kChunkBytesMax = 128ll << 20;
+constexpr int64_t kReadsPerChunkMin = 192, kChunkBytesLongMax = 768ll << 20;  // long reads: see the submit call
 
 struct nrq_slot {
   cudaStream_t stream = nullptr;  // kernels
@@ -433,6 +434,14 @@ int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, cons
 
   int64_t kChunkBytes = (2 * b->raw_off[R] + 4 * b->starts_off[R] + 2 * b->align_off[R] + 7) / 8;
   kChunkBytes = kChunkBytes < kChunkBytesMin ? kChunkBytesMin : kChunkBytes > kChunkBytesMax ? kChunkBytesMax : kChunkBytes;
+  // a chunk's kernels take as long as its slowest read (one warp walks one read: about 30 ms for a 100 kb read), so a
+  // chunk of long reads must hold enough of them to be worth that wait
+  {
+    const int64_t per_read = (2 * b->raw_off[R] + 4 * b->starts_off[R] + 2 * b->align_off[R]) / R;
+    int64_t want = kReadsPerChunkMin * per_read;
+    if (want > kChunkBytesLongMax) want = kChunkBytesLongMax;
+    if (want > kChunkBytes) kChunkBytes = want;
+  }
   if (const char* env = getenv("NRQ_HOST_CHUNK_BYTES")) {
     long long v = atoll(env);
     if (v > 0) kChunkBytes = v;
