@@ -443,3 +443,86 @@ def test_reader_handles_new_style_structures():
     check_structure(hdf5_min.dump_tree(tree))
     assert np.array_equal(again['A'][()], vals) and np.array_equal(again['sub/B'][()], data)
     assert again['A'].attrs['gain'] == 2.5
+
+
+def _random_tree(rng, depth=0):
+    """a random group: attributes, datasets of assorted types (some gzip), sub-groups"""
+    dtypes = ['<i1', '<u1', '<i2', '<u2', '<i4', '<u4', '<i8', '<u8', '<f4', '<f8', 'S1', 'S7',
+              [('a', '<f8'), ('b', '<u4'), ('c', 'S3')], [('x', '<i2'), ('y', '<f4')]]
+    node = {'attrs': {}, 'datasets': {}, 'groups': {}}
+    for k in range(int(rng.integers(0, 5))):
+        kind = int(rng.integers(0, 6))
+        name = 'attr_%d_%s' % (k, 'x' * int(rng.integers(0, 9)))
+        if kind == 0:
+            node['attrs'][name] = int(rng.integers(-2**40, 2**40))
+        elif kind == 1:
+            node['attrs'][name] = float(rng.normal())
+        elif kind == 2:
+            node['attrs'][name] = ''.join(chr(int(c)) for c in rng.integers(0x20, 0x24f, int(rng.integers(0, 20))))
+        elif kind == 3:
+            node['attrs'][name] = np.bytes_(bytes(rng.integers(65, 91, int(rng.integers(1, 12))).astype(np.uint8)))
+        elif kind == 4:
+            node['attrs'][name] = rng.integers(0, 100, int(rng.integers(1, 6))).astype(rng.choice(['<i4', '<u2', '<f8']))
+        else:
+            node['attrs'][name] = np.float32(rng.normal())
+    for k in range(int(rng.integers(0, 4))):
+        dt = np.dtype(dtypes[int(rng.integers(0, len(dtypes)))])
+        shape = tuple(int(v) for v in rng.integers(0, 40, int(rng.integers(1, 3))))
+        raw = rng.integers(0, 256, int(np.prod(shape)) * dt.itemsize, dtype=np.uint8).tobytes()
+        arr = np.frombuffer(raw, dtype=dt).reshape(shape).copy()
+        node['datasets']['ds_%d' % k] = (arr, bool(rng.integers(0, 2)))
+    if depth < 3:
+        for k in range(int(rng.integers(0, 4 if depth else 12))):
+            node['groups']['grp_%02d' % k] = _random_tree(rng, depth + 1)
+    return node
+
+
+def _write_tree(h5, node):
+    for k, v in node['attrs'].items():
+        h5.attrs[k] = v
+    for k, (arr, gz) in node['datasets'].items():
+        h5.create_dataset(k, data=arr, compression='gzip' if gz else None)
+    for k, sub in node['groups'].items():
+        _write_tree(h5.create_group(k), sub)
+
+
+def _same(a, b):
+    if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+        a, b = np.asarray(a), np.asarray(b)
+        return a.dtype == b.dtype and a.shape == b.shape and a.tobytes() == b.tobytes()
+    return type(a) == type(b) and (a == b or (a != a and b != b)) if not isinstance(a, (str, bytes)) else a == b
+
+
+def _check_tree(h5, node):
+    assert sorted(h5.attrs.keys()) == sorted(node['attrs'])
+    for k, v in node['attrs'].items():
+        got = h5.attrs[k]
+        want = np.int64(v) if isinstance(v, int) else np.float64(v) if isinstance(v, float) else v
+        assert _same(got, want), (k, got, want)
+    assert sorted(h5.keys()) == sorted(list(node['datasets']) + list(node['groups']))
+    for k, (arr, gz) in node['datasets'].items():
+        got = h5[k][()]
+        assert got.dtype == arr.dtype and got.shape == arr.shape and got.tobytes() == arr.tobytes(), k
+    for k, sub in node['groups'].items():
+        _check_tree(h5[k], sub)
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_random_trees_round_trip(tmp_path, native, seed):
+    """random object trees (nested groups up to 12 wide, assorted attribute and dataset types, empty and gzip
+    datasets) survive write -> structural walk -> read -> modify -> read"""
+    rng = np.random.default_rng(7000 + seed)
+    tree = _random_tree(rng)
+    fn = str(tmp_path / 'rand.h5')
+    with fast5_io.open_fast5(fn, 'w') as f:
+        _write_tree(f, tree)
+    check_structure(open(fn, 'rb').read())
+    with fast5_io.open_fast5(fn, 'r') as f:
+        _check_tree(f, tree)
+    extra = _random_tree(rng, depth=2)
+    with fast5_io.open_fast5(fn, 'r+') as f:
+        _write_tree(f.create_group('added_later'), extra)
+    tree['groups']['added_later'] = extra
+    check_structure(open(fn, 'rb').read())
+    with fast5_io.open_fast5(fn, 'r') as f:
+        _check_tree(f, tree)
