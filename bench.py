@@ -425,7 +425,7 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-TRAFFIC_FILE = 'r1u_traffic_100k.json'
+TRAFFIC_FILE = 'r1y_traffic_100k.json'
 STAGE_KERNELS = {'k_align_scan': ('k_align_count', 'k_scan_counts', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
                  'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}
 
