@@ -291,7 +291,7 @@ def gpu_arm(args):
     engine = ResquiggleEngine()
     lib = engine.lib
     dev = engine.device
-    params = ResquiggleParams()
+    params = ResquiggleParams(debug_flags=args.debug_flags)
     pc = params.to_c()
 
     # ---- synthetic reads: `unique` per rank on the host, tiled to `reads` on the device
@@ -327,17 +327,19 @@ def gpu_arm(args):
     sampler.mark_begin()
     launches0 = lib.nrq_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_ms = np.zeros(4)
+    stage_ms5 = np.zeros(5)
     ev0.record()
     for _ in range(args.steps):
-        stage_ms += np.array(engine.run_device_profiled(db, pc, out, ws))
+        stage_ms5 += np.array(engine.run_device_profiled(db, pc, out, ws))
     ev1.record()
     barrier()
     sampler.mark_end()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = lib.nrq_launch_count() - launches0
     clocks = sampler.stop()
-    stage_ms /= max(args.steps, 1)
+    stage_ms5 /= max(args.steps, 1)
+    # the re-segmentation stage is two kernels: speculative first searches (k_speculate), then the walk (k_resegment)
+    stage_ms = np.array([stage_ms5[0], stage_ms5[1], stage_ms5[2] + stage_ms5[3], stage_ms5[4]])
 
     ok = (out.status[:db.n_reads] == 0)
     samples_ok = int((n_samples * ok).sum().item())
@@ -385,6 +387,7 @@ def gpu_arm(args):
             gbs = stage_bytes[name] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             stages[name] = {'ms': float(ms), 'algorithmic_bytes': stage_bytes[name],
                             'gbs': gbs, 'frac': gbs / peak}
+        stages['k_resegment']['parts_ms'] = {'k_speculate': float(stage_ms5[2]), 'k_resegment': float(stage_ms5[3])}
         dom = max(stages, key=lambda k: stages[k]['ms'])
         path_gbs = stage_bytes['path'] / (float(stage_ms.sum()) * 1e-3) / 1e9
         traffic, traffic_src = measured_traffic(args, dom)
@@ -417,17 +420,38 @@ def gpu_arm(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             line['cpu_baseline'] = cpu_baseline_leg(args, reads)
-        if world == 1 and args.fast5_files > 0:
-            line['e2e_fast5'] = fast5_leg(args, reads)
+            if args.divergence_reads > 0:
+                line['tie_order_divergence'] = divergence_leg(args, engine, reads)
+    # ---- FAST5 in, FAST5 out (BASELINE.json configs[2] at this N): every rank on its own files and I/O processes
+    if args.fast5_files > 0:
+        if world > 1:
+            os.environ['NRQ_IO_PROCS'] = str(max(2, host_cores() // world))
+        f5 = fast5_leg(args, reads, barrier)
+        agg = torch.tensor([f5['ok_samples'], f5['files'] - f5['failed_reads'], f5['failed_reads']],
+                           dtype=torch.float64, device=dev)
+        tmax = torch.tensor([f5['seconds']], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            dt = float(tmax.item())
+            f5.update({'value': float(agg[0].item()) / dt, 'reads_per_s': float(agg[1].item()) / dt,
+                       'files': args.fast5_files * world, 'failed_reads': int(agg[2].item()), 'seconds': dt,
+                       'n_gpus': world, 'host_cores': host_cores()})
+            del f5['ok_samples']
+            line['e2e_fast5'] = f5
+            if world == 1 and not args.no_cpu_baseline:
+                line['cpu_baseline_fast5'] = cpu_fast5_leg(args, reads)
+    if rank == 0:
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-TRAFFIC_FILE = 'r1y_traffic_100k.json'
+TRAFFIC_FILE = 'r2a_traffic_100k.json'
 STAGE_KERNELS = {'k_align_scan': ('k_align_count', 'k_scan_counts', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
-                 'k_resegment': ('k_resegment',), 'k_event_table': ('k_event_table',)}
+                 'k_resegment': ('k_speculate', 'k_resegment'), 'k_event_table': ('k_event_table',)}
 
 
 def ncu_capture(args):
@@ -547,7 +571,7 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
     return samples, e2e_ms, h2d, d2h
 
 
-def fast5_leg(args, reads):
+def fast5_leg(args, reads, barrier=None):
     """The re-squiggle worker's whole body (resquiggle.py:403-440 -> 318-401) on FAST5 files on disk: open each
     file and read its raw signal, one device batch through the C ABI, RawGenomeCorrected written back into each
     file.  File access is this repo's own HDF5 reader / writer on NRQ_IO_PROCS host processes.  Alignments are
@@ -584,6 +608,8 @@ def fast5_leg(args, reads):
 
         one_pass()                                   # warm-up: pool start-up, pinned staging, kernels
         fast5_jobs.map_jobs(synth.drop_corrected_job, jobs)      # back to the state prep_fast5 leaves (not timed)
+        if barrier is not None:
+            barrier()
         t0 = time.perf_counter()
         failed = one_pass()
         dt = time.perf_counter() - t0
@@ -593,16 +619,108 @@ def fast5_leg(args, reads):
         f = fast5_io.open_fast5(jobs[0][0], 'r')
         ev = f['/Analyses/RawGenomeCorrected_000/BaseCalled_template/Events'][()]
         f.close()
-        return {'value': ok_samples / dt, 'unit': UNIT, 'reads_per_s': (n - len(failed)) / dt, 'files': n,
+        return {'value': ok_samples / dt, 'ok_samples': ok_samples, 'unit': UNIT,
+                'reads_per_s': (n - len(failed)) / dt, 'files': n, 'batch_reads': rsq.DEVICE_BATCH_READS,
                 'failed_reads': len(failed), 'seconds': dt, 'io_procs': fast5_jobs.io_procs(),
                 'bytes_per_file_in': int(np.mean(sizes)), 'events_rows_file0': int(len(ev)),
                 'setup_seconds': setup_s,
-                'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal read, device batch, RawGenomeCorrected '
-                        'write-back into the same file (hdf5_min.py, gzip level 4); mapper and basecall '
-                        'event parsing not included'}
+                'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal read, device '
+                        'batch, datasets packed into gzip chunks by libnrqio threads, RawGenomeCorrected '
+                        'write-back into the same file (hdf5_min.py); mapper and basecall event parsing not '
+                        'included'}
     finally:
         fast5_jobs.shutdown()
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _cpu_fast5_one(job):
+    """the reference's per-read path with its file work (resquiggle.py:318-401 + :55-137) on one core: FAST5 open
+    and raw signal read, the oracle port, RawGenomeCorrected written with zlib level 4 as h5py does"""
+    from oracle import resquiggle_oracle as orc
+    from nanoraw_b200 import resquiggle as rsq
+    from nanoraw_b200 import nanoraw_helper as nh
+    from nanoraw_b200.frontend import genomeLoc, readInfo
+    fn, read = job
+    t0 = time.perf_counter()
+    try:
+        _, raw, _, _ = rsq._read_raw_inputs(fn, 'median', 'Basecall_1D_000', 'BaseCalled_template')
+        out = orc.resquiggle_read(raw, read.read_start_rel_to_raw, read.starts, read.read_align.decode(),
+                                  read.genome_align.decode(), sort_kind='default', verbatim_clip_loop=True)
+        ev = np.empty(len(out['events']['start']), dtype=np.dtype(rsq.EVENT_DTYPE))
+        for col in ('norm_mean', 'norm_stdev', 'start', 'length', 'base'):
+            ev[col] = out['events'][col]
+        rsq.write_new_fast5_group(
+            fn, genomeLoc(int(read.genome_start), read.strand, read.chrom),
+            readInfo(os.path.basename(fn), 'BaseCalled_template', 0, 0, 0, 0, 0, 0),
+            int(read.read_start_rel_to_raw), out['new_segs'], ev['base'].tobytes().decode(),
+            (read.read_align, read.genome_align), read.starts, None, nh.scaleValues(*out['scale_values']),
+            'RawGenomeCorrected_000', 'BaseCalled_template', 'median', 5, True, event_data=ev)
+        ok = True
+    except Exception:
+        ok = False
+    return read.n_samples if ok else 0, time.perf_counter() - t0
+
+
+def cpu_fast5_leg(args, reads):
+    """CPU figure that includes the file work, next to e2e_fast5: a bounded sample of the same files"""
+    import multiprocessing as mp
+    import shutil
+    import tempfile
+    cores = host_cores()
+    n = min(len(reads), max(8, 8 * cores if args.cpu_reads is None else args.cpu_reads))
+    tmp = tempfile.mkdtemp(prefix='nrq_cpu_fast5_')
+    try:
+        jobs = [(os.path.join(tmp, 'read_%05d.fast5' % i), reads[i]) for i in range(n)]
+        with mp.get_context('fork').Pool(cores) as pool:
+            pool.map(synth.write_basecalled_fast5_job, jobs)
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_fast5_one, jobs, chunksize=1)
+            dt = time.perf_counter() - t0
+        samples = sum(s for s, _ in res)
+        cpu_s = sum(t for _, t in res)
+        return {'value': samples / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                'sample': '%d FAST5 files of the same workload (%d samples), %.1f s wall, %.1f CPU-s: file read + '
+                          'oracle port + RawGenomeCorrected write (zlib level 4, as h5py)' % (n, samples, dt, cpu_s),
+                'per_core': samples / cpu_s if cpu_s > 0 else None}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def _divergence_one(args):
+    """per read: boundaries of the deterministic order (what the GPU must equal) and of numpy's default argsort"""
+    from oracle import resquiggle_oracle as orc
+    read, gpu_segs = args
+    try:
+        d = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts, read.read_align.decode(),
+                                read.genome_align.decode(), sort_kind='default')['new_segs']
+    except Exception:
+        return 0, 0, 0
+    if len(d) != len(gpu_segs):
+        return len(d), len(d), 1
+    diff = int((np.asarray(d) != np.asarray(gpu_segs)).sum())
+    return len(d), diff, int(diff > 0)
+
+
+def divergence_leg(args, engine, reads):
+    """BASELINE.json: 'any float64 near-tie divergence logged and bounded'.  The reference visits running
+    differences in numpy's default (unstable) argsort order (resquiggle.py:246); the device path is held to the
+    deterministic order.  Fraction of boundaries of the GPU output that differ from the reference order on THIS
+    host's numpy, over the first --divergence-reads reads of the workload."""
+    import multiprocessing as mp
+    from nanoraw_b200.batch import ReadBatch
+    from nanoraw_b200.engine import ResquiggleParams
+    n = min(len(reads), args.divergence_reads)
+    sub = reads[:n]
+    res = engine.run(ReadBatch.from_reads(sub), ResquiggleParams())
+    jobs = [(rd, res.new_segs_of(r)) for r, rd in enumerate(sub) if res.ok(r)]
+    with mp.get_context('fork').Pool(host_cores()) as pool:
+        out = pool.map(_divergence_one, jobs, chunksize=4)
+    total = sum(a for a, _, _ in out)
+    diff = sum(b for _, b, _ in out)
+    return {'reads': len(jobs), 'boundaries': total, 'differing_boundaries': diff,
+            'fraction': diff / total if total else None, 'reads_affected': sum(c for _, _, c in out),
+            'against': "oracle port with sort_kind='default' (numpy %s argsort on this host); the GPU output "
+                       "equals sort_kind='stable' bit for bit (tests/)" % np.__version__}
 
 
 def cpu_baseline_leg(args, reads):
@@ -622,16 +740,21 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=('ours', 'reference'))
     ap.add_argument('--reads', type=int, default=100_000, help='reads per GPU')
-    ap.add_argument('--unique', type=int, default=2000, help='distinct synthetic reads generated on the host')
+    ap.add_argument('--unique', type=int, default=4000, help='distinct synthetic reads generated on the host')
     ap.add_argument('--config', default='standard', choices=('standard', 'short', 'long', 'dense'))
-    ap.add_argument('--e2e-steps', type=int, default=8)
+    ap.add_argument('--e2e-steps', type=int, default=None, help='steps of the e2e leg (default: --steps)')
     ap.add_argument('--e2e-reps', type=int, default=4, help='unique reads repeated this often in one e2e call')
     ap.add_argument('--cpu-reads', type=int, default=None)
     ap.add_argument('--ref-reads', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--fast5-files', type=int, default=2048,
-                    help='FAST5 files on disk for the e2e_fast5 leg (N = 1 only; 0 = skip)')
+    ap.add_argument('--debug-flags', type=int, default=0, help='nrq_params.debug_flags (4 = no speculative search)')
+    ap.add_argument('--fast5-files', type=int, default=4096,
+                    help='FAST5 files on disk per GPU for the e2e_fast5 leg (0 = skip)')
+    ap.add_argument('--divergence-reads', type=int, default=1024,
+                    help='reads compared with the reference\'s default argsort order (N = 1; 0 = skip)')
     args = ap.parse_args()
+    if args.e2e_steps is None:
+        args.e2e_steps = max(args.steps, 1)
     claim_stdout()
     if args.impl == 'reference':
         reference_arm(args)

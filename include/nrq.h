@@ -68,7 +68,8 @@ typedef struct nrq_params {
   int32_t big_region_cap;   /* samples per warp of global scratch for regions that do not fit shared memory */
   int32_t debug_flags;      /* bit0: force the general (bisection) order-statistic path in nrq_norm_stats;
                                bit1: event statistics in numpy's float64 summation order (bit-identical to
-                               numpy, slower) instead of exact integer prefix sums (within a few ulps) */
+                               numpy, slower) instead of exact integer prefix sums (within a few ulps);
+                               bit2: no speculative first search in nrq_resegment (walk only; same results, slower) */
 } nrq_params;
 
 /* Ragged batch, inputs.  R = n_reads.
@@ -147,14 +148,17 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
                          const int64_t* norm_off, double* norm_signal, void* stream);
 
 /* a3-a6: get_indel_groups + splice (resquiggle.py:203-316, 362-387) -> new_segs, status.
- * group_scratch: int32[4*indel_capacity]; big_scratch: see nrq_workspace_bytes; region_samples and n_groups may be NULL.
+ * group_scratch: int32[4*indel_capacity]; spec_scratch: int32[4*spec_capacity] or NULL, spec_capacity >= the
+ * number of indels of the batch (scratch of the speculative first search of every group, which runs ahead of the
+ * read-by-read walk; NULL = walk only, same results);
+ * work_counter: int32[2]; big_scratch: see nrq_workspace_bytes; region_samples and n_groups may be NULL.
  * On return group_scratch holds, per read at int4 index indel_off[r], n_groups[r] records
  * (group_start, group_stop, first indel index, max indel end) = the reference's indelGroupStats. */
 int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                   const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
-                  int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
-                  int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
-                  int32_t* n_groups, void* stream);
+                  int32_t* group_scratch, int32_t* spec_scratch, int64_t spec_capacity, double* big_scratch,
+                  int64_t big_scratch_doubles, int32_t* work_counter, int32_t* status, int32_t* new_segs,
+                  int32_t* region_samples, int32_t* n_groups, void* stream);
 
 /* f-4: the running-difference trace of plot_correction (plot_commands.py:225-229) over one window of an already
  * normalised signal (device pointers): out[i] = |2 cs[i+m] - cs[i] - cs[i+2m]|, i in [0, n - 2m], cs the
@@ -186,8 +190,8 @@ int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_resu
                          void* workspace, int64_t workspace_bytes, void* stream);
 
 /* nrq_resquiggle_batch with CUDA events recorded on `stream` around each stage; waits for the batch and
- * writes the device time in ms of {indel scan (a2), order statistics (a1), re-segmentation (a3-a6),
- * event table (a7)} to stage_ms[4].  Measurement aid for bench.py. */
+ * writes the device time in ms of {indel scan (a2), order statistics (a1), re-segmentation (a3-a6): speculative
+ * first searches, then the walk, event table (a7)} to stage_ms[5].  Measurement aid for bench.py. */
 int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
                                  void* workspace, int64_t workspace_bytes, void* stream, float* stage_ms);
 

@@ -47,8 +47,8 @@ SYMBOLS = {
     'nrq_find_indels': (C.c_int, [C.POINTER(NrqBatch), _P, _P, _P, _P, _P, C.c_int64, _P, _P]),
     'nrq_norm_stats': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P]),
     'nrq_normalize_signal': (C.c_int, [C.POINTER(NrqBatch), _P, _P, _P, _P, _P]),
-    'nrq_resegment': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
-                                C.c_int64, _P, _P, _P, _P, _P, _P]),
+    'nrq_resegment': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P, C.c_int64,
+                                _P, C.c_int64, _P, _P, _P, _P, _P, _P]),
     'nrq_running_diffs': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     'nrq_genome_aggregate': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                        _P, _P, _P]),

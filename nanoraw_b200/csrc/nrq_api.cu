@@ -1,6 +1,7 @@
 // C ABI of libnrq.so (include/nrq.h).  Unity build: the kernels live in the .cu files included
 // below; this file only validates arguments, carves the workspace and launches.
 #include <atomic>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,6 +10,7 @@
 
 #include "nrq_indels.cu"
 #include "nrq_norm.cu"
+#include "nrq_speculate.cu"
 #include "nrq_resegment.cu"
 #include "nrq_events.cu"
 #include "nrq_aggregate.cu"
@@ -36,18 +38,46 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-int resegment_grid(int n_reads) {
-  static int cached = 0;
-  if (!cached) {
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
+// device-filling grids of the two persistent kernels, worked out once per device (a process may drive several)
+struct DeviceGrids {
+  bool ready = false;
+  int seg = 1;   // k_resegment: CTAs resident on the whole device
+  int spec = 1;  // k_speculate
+};
+constexpr int kMaxDevices = 64;
+
+const DeviceGrids& device_grids() {
+  static DeviceGrids grids[kMaxDevices];
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  DeviceGrids& g = grids[dev];
+  if (!g.ready) {
+    int sms = 148, per_sm = 1;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrq::k_resegment, nrq::kSegWarps * 32, 0);
-    if (per_sm < 1) per_sm = 1;
-    cached = sms * per_sm;
+    g.seg = sms * (per_sm < 1 ? 1 : per_sm);
+    cudaFuncSetAttribute(nrq::k_speculate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(nrq::SpecSm));
+    per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, nrq::k_speculate, nrq::kSpecThreads,
+                                                  sizeof(nrq::SpecSm));
+    g.spec = sms * (per_sm < 1 ? 1 : per_sm);
+    g.ready = true;
   }
+  return g;
+}
+
+int resegment_grid(int n_reads) {
+  const int cached = device_grids().seg;
   int need = (n_reads + nrq::kSegWarps - 1) / nrq::kSegWarps;
   return need < cached ? (need > 0 ? need : 1) : cached;
+}
+
+int speculate_grid(int n_reads) {
+  const int cached = device_grids().spec;
+  return n_reads < cached ? (n_reads > 0 ? n_reads : 1) : cached;
 }
 
 struct Workspace {
@@ -55,6 +85,7 @@ struct Workspace {
   int32_t* work_counter;
   int32_t* indels;
   int32_t* groups;
+  int32_t* spec;
   int64_t indel_cap;
   double* big;
   int64_t big_doubles;
@@ -75,6 +106,8 @@ Workspace carve(void* base, int32_t n_reads, int64_t total_align, const nrq_para
   w.indels = reinterpret_cast<int32_t*>(b + off);
   off = align_up(off + 16 * indel_cap, 256);
   w.groups = reinterpret_cast<int32_t*>(b + off);
+  off = align_up(off + 16 * indel_cap, 256);
+  w.spec = reinterpret_cast<int32_t*>(b + off);
   off = align_up(off + 16 * indel_cap, 256);
   int grid = resegment_grid(n_reads);
   w.big_doubles = (int64_t)grid * nrq::kSegWarps * ((int64_t)p->big_region_cap + 1);
@@ -190,11 +223,14 @@ int nrq_normalize_signal(const nrq_batch* b, const double* scale_values, const i
   return 0;
 }
 
-int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
-                  const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
-                  int32_t* group_scratch, double* big_scratch, int64_t big_scratch_doubles,
-                  int32_t* work_counter, int32_t* status, int32_t* new_segs, int32_t* region_samples,
-                  int32_t* n_groups, void* stream) {
+}  // extern "C"
+
+// `mid` (optional): recorded between the speculative search and the walk
+static int resegment_impl(const nrq_batch* b, const nrq_params* p, const double* scale_values,
+                          const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
+                          int32_t* group_scratch, int32_t* spec_scratch, int64_t spec_capacity, double* big_scratch,
+                          int64_t big_scratch_doubles, int32_t* work_counter, int32_t* status, int32_t* new_segs,
+                          int32_t* region_samples, int32_t* n_groups, void* stream, cudaEvent_t mid) {
   if (int e = check_batch(b)) return e;
   if (int e = check_params(p)) return e;
   if (!scale_values || !indel_off || !indels || !n_bases || !group_scratch || !work_counter || !status ||
@@ -206,14 +242,40 @@ int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_v
   int64_t need = (int64_t)grid * nrq::kSegWarps * ((int64_t)p->big_region_cap + 1);
   if (p->big_region_cap > 0 && (!big_scratch || big_scratch_doubles < need))
     return fail("nrq_resegment: big_scratch too small");
-  cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(int32_t), s);
+  cudaError_t e = cudaMemsetAsync(work_counter, 0, 2 * sizeof(int32_t), s);
   if (e != cudaSuccess) return fail("memset work_counter", e);
+  // K2a: first change-point search of every indel group, one region per thread (nrq_speculate.cu).  Optional:
+  // whatever it does not cover is searched by k_resegment.  debug_flags bit 2 turns it off (tests compare both).
+  const bool speculate = spec_scratch && spec_capacity > 0 && !b->norm_signal && p->min_seg_len == nrq::kSpecM && !(p->debug_flags & 4);
+  // spec_scratch: an int2 entry per indel, then kSpecCptBytesPerIndel bytes per indel for the found change-points
+  int2* spec_entries = reinterpret_cast<int2*>(spec_scratch);
+  unsigned char* spec_bytes = reinterpret_cast<unsigned char*>(spec_scratch) + 8 * spec_capacity;
+  if (speculate) {
+    nrq::k_speculate<<<speculate_grid(b->n_reads), nrq::kSpecThreads, sizeof(nrq::SpecSm), s>>>(
+        *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), work_counter + 1, status,
+        spec_entries, spec_bytes);
+    NRQ_CHECK_LAUNCH("k_speculate");
+  }
+  if (mid) cudaEventRecord(mid, s);
   nrq::k_resegment<<<grid, nrq::kSegWarps * 32, 0, s>>>(
       *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), n_bases,
       reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs, region_samples,
-      n_groups);
+      n_groups, speculate ? spec_entries : nullptr, spec_bytes);
   NRQ_CHECK_LAUNCH("k_resegment");
   return 0;
+}
+
+extern "C" {
+
+int nrq_resegment(const nrq_batch* b, const nrq_params* p, const double* scale_values,
+                  const int64_t* indel_off, const int32_t* indels, const int32_t* n_bases,
+                  int32_t* group_scratch, int32_t* spec_scratch, int64_t spec_capacity, double* big_scratch,
+                  int64_t big_scratch_doubles, int32_t* work_counter, int32_t* status, int32_t* new_segs,
+                  int32_t* region_samples, int32_t* n_groups, void* stream) {
+  return resegment_impl(b, p, scale_values, indel_off, indels, n_bases, group_scratch, spec_scratch, spec_capacity,
+                        big_scratch,
+                        big_scratch_doubles, work_counter, status, new_segs, region_samples, n_groups, stream,
+                        nullptr);
 }
 
 int nrq_running_diffs(const double* signal, int32_t n, int32_t min_seg_len, double* scratch, double* out,
@@ -278,7 +340,7 @@ static int resquiggle_batch_impl(const nrq_batch* b, const nrq_params* p, const 
   Workspace probe = carve(nullptr, b->n_reads, 0, p, 0);
   int64_t spare = workspace_bytes - probe.bytes - 1024;
   if (spare < 32) return fail("nrq_resquiggle_batch: workspace too small");
-  int64_t indel_cap = spare / 32;
+  int64_t indel_cap = spare / 48;
   Workspace w = carve(workspace, b->n_reads, 0, p, indel_cap);
   if (w.bytes > workspace_bytes) return fail("nrq_resquiggle_batch: workspace too small");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -291,8 +353,9 @@ static int resquiggle_batch_impl(const nrq_batch* b, const nrq_params* p, const 
   mark(1);
   if (int e = nrq_norm_stats(b, p, out->status, out->scale_values, stream)) return e;
   mark(2);
-  if (int e = nrq_resegment(b, p, out->scale_values, w.indel_off, w.indels, out->n_bases, w.groups, w.big,
-                            w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, nullptr, stream))
+  if (int e = resegment_impl(b, p, out->scale_values, w.indel_off, w.indels, out->n_bases, w.groups, w.spec, w.indel_cap, w.big,
+                             w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, nullptr,
+                             stream, ev ? ev[5] : nullptr))
     return e;
   mark(3);
   if (int e = nrq_event_table(b, p, out->scale_values, out->n_bases, out->new_segs, out->status, out->norm_mean,
@@ -310,7 +373,7 @@ int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_resu
 int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const nrq_results* out,
                                  void* workspace, int64_t workspace_bytes, void* stream, float* stage_ms) {
   if (!stage_ms) return fail("nrq_resquiggle_batch_profile: stage_ms is NULL");
-  thread_local cudaEvent_t ev[5];
+  thread_local cudaEvent_t ev[6];  // 0..4 around the stages, 5 between the two kernels of the re-segmentation
   thread_local bool have = false;
   if (!have) {
     for (auto& e : ev)
@@ -320,7 +383,11 @@ int nrq_resquiggle_batch_profile(const nrq_batch* b, const nrq_params* p, const 
   if (int e = resquiggle_batch_impl(b, p, out, workspace, workspace_bytes, stream, ev)) return e;
   cudaError_t ce = cudaEventSynchronize(ev[4]);
   if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_profile: sync", ce);
-  for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+  cudaEventElapsedTime(&stage_ms[0], ev[0], ev[1]);
+  cudaEventElapsedTime(&stage_ms[1], ev[1], ev[2]);
+  cudaEventElapsedTime(&stage_ms[2], ev[2], ev[5]);
+  cudaEventElapsedTime(&stage_ms[3], ev[5], ev[3]);
+  cudaEventElapsedTime(&stage_ms[4], ev[3], ev[4]);
   return 0;
 }
 

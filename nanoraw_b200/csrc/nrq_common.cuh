@@ -8,6 +8,10 @@
 
 #define NRQ_GAP 45  // '-'
 
+namespace nrq {
+constexpr unsigned kFull = 0xffffffffu;  // all lanes of a warp
+}
+
 struct NormCoef {
   double shift, scale, lo, hi;
   int clip;

@@ -25,7 +25,6 @@ constexpr int kSegWarps = 8;
 #endif
 constexpr int kRegionCap = NRQ_SEG_CAP;  // region samples held in shared memory per warp (p99 of real regions ~200)
 constexpr int kSegLut = NRQ_SEG_LUT;     // DAC codes covered by the per-warp table of normalised values
-constexpr unsigned kFull = 0xffffffffu;
 
 struct SegCtx {
   const int32_t* t;   // starts_rel_to_read
@@ -47,6 +46,8 @@ struct SegCtx {
   const double* lut;  // normalised value of DAC code lut_lo + k
   unsigned* picks;    // this warp's picks of one selection, in pick order (shared memory)
   int lut_lo;
+  const int2* spec;     // K2a's outcome per group head (nrq_speculate.cu) or nullptr
+  const unsigned char* cpt_bytes;  // K2a's change-points of this read, as byte offsets from the region start
 };
 
 // extend_group, resquiggle.py:203-216
@@ -283,12 +284,20 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
 
 // extend_for_cpts (:256-276) for a group whose extend_group result is already known, preceded by the merge
 // loop of extend_and_join (:220-225)
+// known_none: K2a searched exactly this (start, stop, K) and found None; only honoured if no merge happens first
 __device__ __forceinline__ int search_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop,
-                                            int K, int t_start, int t_stop) {
+                                            int K, int t_start, int t_stop, bool known_none = false) {
+  if (start <= c.top_stop) known_none = false;
   int st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
   if (st != NRQ_ST_OK) return st;
   for (;;) {
-    int res = get_cpts(c, t_start, t_stop, K, start + c.ind[lo].w + 1);
+    int res = 0;
+    if (known_none) {
+      if (c.limit >= 0 && K > c.limit) return NRQ_ST_CPTS_LIMIT;
+      known_none = false;
+    } else {
+      res = get_cpts(c, t_start, t_stop, K, start + c.ind[lo].w + 1);
+    }
     if (res > 0) return NRQ_ST_OK;
     if (res < 0) return -res;
     if (start == 0 && stop == c.last) return NRQ_ST_UNSATISFIABLE;
@@ -437,6 +446,10 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     const int gmax = __shfl_sync(kFull, M, e);
     const int zsum = __shfl_sync(kFull, my.w + my.z, e);
     const bool planned = brk && valid && complete;
+    int2 spw = make_int2(0, 0);
+    if (c.spec && valid) spw = c.spec[k + lane];
+    bool sp_found = false, sp_none = false;
+    int p_start = 0, p_stop = 0, p_K = 0;  // this lane's plan, if it heads a planned group
     if (planned) {  // extend_group (:203-216) for the group lane .. e
       int start = my.x, stop = gmax, st = NRQ_ST_OK;
       int K = (zsum - my.w) + stop - start - 1;
@@ -450,12 +463,49 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       }
       if (K < 0 || K >= (1 << kPlanKBits)) { st = kPlanGeneric; K = 0; }
       c.groups[k + lane] = make_int4(start, stop, K | ((e - lane) << kPlanKBits) | (st << (kPlanKBits + 5)), gmax);
+      p_start = start; p_stop = stop; p_K = K;
+      // K2a's result counts only if it searched this very plan
+      if (st == NRQ_ST_OK && K >= 1 && K <= kSpecMaxK && stop - start <= 255 && e - lane <= kSpecMaxLen) {
+        sp_found = spw.x == spec_word(kSpecFound, K, start, stop);
+        sp_none = spw.x == spec_word(kSpecNone, K, start, stop);
+      }
     }
+    const unsigned found_mask = __ballot_sync(kFull, sp_found), none_mask = __ballot_sync(kFull, sp_none);
     unsigned todo = __ballot_sync(kFull, planned);
     __syncwarp();
-    // ---- walk the planned groups; whatever cannot be taken from a plan goes indel by indel (one call site below)
     int next_k = k;
     bool drive = todo == 0u;  // more than 32 indels in one group
+    // ---- the leading planned groups that K2a has already searched successfully, that begin behind the group before
+    // them (:220: no merge) and end before the next indel (:299: not left open) are finished as they stand: all of
+    // them at once, one lane per group (stack entry, change-points copied into their new_segs slots).  The stack
+    // entries land below the parked record of every group that is still to be walked (at most one finished group
+    // per consumed indel).
+    if (c.spec) {
+      const unsigned before = todo & ((1u << lane) - 1u);
+      const int prev_lane = before ? 31 - __clz(before) : 0;
+      const int prev_sh = __shfl_sync(kFull, p_stop, prev_lane);
+      const int prev_stop = before ? prev_sh : c.top_stop;
+      const int nxt_x = __shfl_sync(kFull, my.x, (e + 1) & 31);  // a planned group ends inside the window
+      const bool clean = sp_found && p_start > prev_stop && p_stop < nxt_x;
+      const unsigned bad = todo & ~__ballot_sync(kFull, clean);
+      const unsigned prefix = bad ? todo & ((1u << (__ffs(bad) - 1)) - 1u) : todo;
+      if (prefix) {
+        if ((prefix >> lane) & 1u) {
+          c.groups[c.ng + __popc(prefix & ((1u << lane) - 1u))] = make_int4(p_start, p_stop, k + lane, gmax);
+          const int t0 = c.t[p_start];
+          int32_t* o = c.out + p_start + my.w + 1;
+          const unsigned char* src = c.cpt_bytes + spw.y;
+          for (int i = 0; i < p_K; ++i) o[i] = t0 + (int)src[i];
+        }
+        const int last_lane = 31 - __clz(prefix);
+        c.ng += __popc(prefix);
+        c.top_stop = __shfl_sync(kFull, p_stop, last_lane);
+        next_k = k + __shfl_sync(kFull, e, last_lane) + 1;
+        todo &= ~prefix;
+        __syncwarp();
+      }
+    }
+    // ---- walk the planned groups; whatever cannot be taken from a plan goes indel by indel (one call site below)
     int d_lo = k, d_hi = k, d_maxend = 0, d_k = k + 1;
     if (drive) d_maxend = c.ind[k].y;
     while (todo) {
@@ -472,8 +522,17 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
         break;
       }
       if (st != NRQ_ST_OK) return st;
-      st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop]);
-      if (st != NRQ_ST_OK) return st;
+      const int cpt_off = __shfl_sync(kFull, spw.y, s);
+      if (((found_mask >> s) & 1u) && start > c.top_stop) {  // searched by K2a, and no finished group in the way
+        const int K = rec.z & ((1 << kPlanKBits) - 1);
+        const int t0 = c.t[start];
+        int32_t* o = c.out + start + c.ind[lo].w + 1;
+        for (int i = lane; i < K; i += 32) o[i] = t0 + (int)c.cpt_bytes[cpt_off + i];
+      } else {
+        st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop],
+                          (none_mask >> s) & 1u);
+        if (st != NRQ_ST_OK) return st;
+      }
       if (hi + 1 < c.n_ind) {
         const int4 nxt = c.ind[hi + 1];
         if (stop >= nxt.x) {  // :299-300: the finished group reaches the next indel and stays open
@@ -484,6 +543,7 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       }
       push_group(c, start, stop, lo, maxend);
       next_k = hi + 1;
+      if (c.spec) break;  // plan again from here: whatever follows is most likely finished in one go as well
     }
     if (drive) {
       int st = drive_until_push(c, d_k, d_lo, d_hi, d_maxend);
@@ -518,7 +578,8 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
             const int4* __restrict__ indels, const int32_t* __restrict__ n_bases, int4* __restrict__ group_scratch,
             double* __restrict__ big_scratch, int32_t* __restrict__ work_counter, int32_t* __restrict__ status,
             int32_t* __restrict__ new_segs, int32_t* __restrict__ region_samples,
-            int32_t* __restrict__ n_groups) {
+            int32_t* __restrict__ n_groups, const int2* __restrict__ spec,
+            const unsigned char* __restrict__ spec_bytes) {
   struct WarpSm {
     double region[kRegionCap + 2];
     double lut[kSegLut];
@@ -552,6 +613,8 @@ k_resegment(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     c.ng = 0;
     c.top_stop = -1;
     c.out = new_segs + b.align_off[r] + r;
+    c.spec = spec ? spec + indel_off[r] : nullptr;
+    c.cpt_bytes = spec ? spec_bytes + (size_t)kSpecCptBytesPerIndel * (size_t)indel_off[r] : nullptr;
     // the two pointers the state machine dereferences most are pinned in vector registers; as warp-uniform
     // values the compiler otherwise re-forms their addresses on the uniform datapath at every use (4 instructions)
     asm volatile("" : "+l"(c.t));

@@ -208,10 +208,10 @@ class ResquiggleEngine(object):
         return out
 
     def run_device_profiled(self, dbatch, params, out, workspace):
-        """run_device, plus the device time (ms) of each of the four stages (CUDA events on the
-        launching stream); returns after the batch has finished."""
+        """run_device, plus the device time (ms) of {indel scan, order statistics, speculative searches, walk,
+        event table} (CUDA events on the launching stream); returns after the batch has finished."""
         pc = params.to_c() if isinstance(params, ResquiggleParams) else params
-        ms = (C.c_float * 4)()
+        ms = (C.c_float * 5)()
         with self.torch.cuda.device(self.device):
             rc = self.lib.nrq_resquiggle_batch_profile(
                 C.byref(dbatch.c), C.byref(pc), C.byref(out.c), _ptr(workspace), workspace.numel(),
@@ -281,7 +281,11 @@ class ResquiggleEngine(object):
         if R:
             rc = self.lib.nrq_resquiggle_batch_host(self._host_handle(), C.byref(hb), C.byref(pc), C.byref(hr))
             _lib.check(rc, 'nrq_resquiggle_batch_host')
-        return HostResults(np.asarray(src.align_off[:R + 1]), outs)
+        res = HostResults(np.asarray(src.align_off[:R + 1]), outs)
+        # the C structs (host pointers) of this batch, for callers that hand the results on through the C ABI
+        # (libnrqio's chunk packing); `keep` pins the arrays they point at
+        res.c_batch, res.c_results, res._keep = hb, hr, keep
+        return res
 
     def run(self, batch, params):
         """Host arrays in, host arrays out (ReadBatch -> HostResults)."""
@@ -388,8 +392,8 @@ class ResquiggleEngine(object):
             ng = t.zeros(1, dtype=t.int32, device=self.device)
             rc = self.lib.nrq_resegment(
                 C.byref(db.c), C.byref(pc), _ptr(sv), _ptr(d_off), _ptr(d_ind), _ptr(d_nb), _ptr(groups),
-                _ptr(big), big.numel(), _ptr(counter), _ptr(d_status), _ptr(segs), C.c_void_p(0), _ptr(ng),
-                self._stream())
+                C.c_void_p(0), 0, _ptr(big), big.numel(), _ptr(counter), _ptr(d_status), _ptr(segs), C.c_void_p(0),
+                _ptr(ng), self._stream())
             _lib.check(rc, 'nrq_resegment')
         st = int(d_status.cpu()[0])
         out = []

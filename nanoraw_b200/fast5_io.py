@@ -29,12 +29,17 @@ def set_backend(name):
     _BACKEND[0] = name
 
 
+_H5PY = []
+
+
 def _have_h5py():
-    try:
-        import h5py  # noqa: F401
-        return True
-    except Exception:
-        return False
+    if not _H5PY:  # asked on every open: a failed import is not cached by Python and costs half a millisecond
+        try:
+            import h5py  # noqa: F401
+            _H5PY.append(True)
+        except Exception:
+            _H5PY.append(False)
+    return _H5PY[0]
 
 
 def _split(path):
@@ -112,6 +117,39 @@ class LazyDataset(MemDataset):
     @property
     def dtype(self):
         return self._dtype
+
+
+class _PackedLoader(object):
+    """a dataset that exists as its gzip chunk (zlib stream): inflated only if somebody reads it"""
+
+    def __init__(self, payload, dtype, shape):
+        self.payload, self.dtype, self.shape = payload, dtype, shape
+
+    def __call__(self):
+        import zlib
+        return np.frombuffer(zlib.decompress(self.payload), dtype=self.dtype).reshape(self.shape)
+
+    def stored_chunk(self):
+        return self.payload
+
+
+def create_packed_dataset(group, name, shape, dtype, payload):
+    """group.create_dataset(name, data=..., compression='gzip') for data that is already one gzip chunk (a zlib
+    stream of the C-order bytes): the native and mem backends keep the chunk as it is, h5py writes it with
+    write_direct_chunk.  Returns the dataset."""
+    dtype = np.dtype(dtype)
+    shape = tuple(int(v) for v in shape)
+    if isinstance(group, (MemGroup, MemFile)) or hasattr(group, '_children'):
+        parts = _split(name)
+        parent = group._walk('/'.join(parts[:-1]), create=True)
+        if parts[-1] in parent._children:
+            raise ValueError('Unable to create dataset (name already exists)')
+        ds = LazyDataset(_PackedLoader(bytes(payload), dtype, shape), dtype, shape, compression='gzip')
+        parent._children[parts[-1]] = parent._adopt(ds)
+        return ds
+    ds = group.create_dataset(name, shape=shape, dtype=dtype, chunks=shape, compression='gzip')  # h5py
+    ds.id.write_direct_chunk((0,) * len(shape), bytes(payload))
+    return ds
 
 
 class MemGroup(object):

@@ -72,6 +72,16 @@ def write_job(args):
         return str(e)
 
 
+def write_packed_job(args):
+    """write_packed_fast5_group(*args) -> None | error message"""
+    from . import resquiggle
+    try:
+        resquiggle.write_packed_fast5_group(*args)
+        return None
+    except Exception as e:  # noqa: BLE001
+        return str(e)
+
+
 def start_jobs(fn, jobs):
     """submit fn over jobs and return at once: an iterable of the results, in order, that blocks as it is read"""
     p = pool()

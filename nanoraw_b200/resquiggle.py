@@ -34,7 +34,7 @@ from .frontend import (  # noqa: F401  (re-exported call surface)
 VERBOSE = False
 
 # reads per device batch in the re-squiggle worker (additive knob, not a reference option)
-DEVICE_BATCH_READS = int(os.environ.get('NANORAW_B200_BATCH_READS', '512'))
+DEVICE_BATCH_READS = int(os.environ.get('NANORAW_B200_BATCH_READS', '4096'))
 
 indelStats = namedtuple('indelStats', ('start', 'end', 'diff'))  # :29-30
 indelGroupStats = namedtuple('indelGroupStats', ('start', 'end', 'cpts', 'indels'))  # :31-32
@@ -116,6 +116,47 @@ def write_new_fast5_group(
     except Exception:
         raise NotImplementedError(msg.WRITE_BACK)
 
+    try:
+        read_data.flush()
+        read_data.close()
+    except Exception:
+        raise NotImplementedError(msg.CLOSE_AFTER_WRITE)
+    return
+
+
+def write_packed_fast5_group(
+        filename, genome_location, read_info, read_start_rel_to_raw, packed, scale_values, corrected_group,
+        basecall_subgroup, norm_type, outlier_thresh):
+    """write_new_fast5_group (resquiggle.py:80-135) for a read whose four datasets already exist as gzip chunks
+    (libnrqio, nrqio_pack_corrected): `packed` = (n_bases, n_align, n_segs, Events chunk, read_alignment chunk,
+    genome_alignment chunk, read_segments chunk).  Same groups, attributes, dataset names, dtypes and filter as
+    the reference writes; same error messages."""
+    n_bases, n_align, n_segs, ev_chunk, ra_chunk, ga_chunk, seg_chunk = packed
+    try:
+        read_data = fast5_io.open_fast5(filename, 'r+')
+    except Exception:
+        raise NotImplementedError(msg.OPEN_FOR_WRITE)
+    try:
+        subgroup = read_data['/Analyses/' + corrected_group].create_group(basecall_subgroup)
+        for key, value in (('shift', scale_values.shift), ('scale', scale_values.scale),
+                           ('lower_lim', scale_values.lower_lim), ('upper_lim', scale_values.upper_lim),
+                           ('norm_type', norm_type), ('outlier_threshold', outlier_thresh)):
+            subgroup.attrs[key] = value
+        alignment = subgroup.create_group('Alignment')
+        for key, value in (
+                ('mapped_start', genome_location.Start), ('mapped_strand', genome_location.Strand),
+                ('mapped_chrom', genome_location.Chrom),
+                ('clipped_bases_start', read_info.ClipStart), ('clipped_bases_end', read_info.ClipEnd),
+                ('num_insertions', read_info.Insertions), ('num_deletions', read_info.Deletions),
+                ('num_matches', read_info.Matches), ('num_mismatches', read_info.Mismatches)):
+            alignment.attrs[key] = value
+        fast5_io.create_packed_dataset(alignment, 'read_alignment', (n_align,), 'S1', ra_chunk)
+        fast5_io.create_packed_dataset(alignment, 'genome_alignment', (n_align,), 'S1', ga_chunk)
+        fast5_io.create_packed_dataset(alignment, 'read_segments', (n_segs,), '<i8', seg_chunk)
+        events = fast5_io.create_packed_dataset(subgroup, 'Events', (n_bases,), np.dtype(EVENT_DTYPE), ev_chunk)
+        events.attrs['read_start_rel_to_raw'] = read_start_rel_to_raw
+    except Exception:
+        raise NotImplementedError(msg.WRITE_BACK)
     try:
         read_data.flush()
         read_data.close()
@@ -245,6 +286,12 @@ class BatchPipeline(object):
             compute_sd=self.compute_sd, num_cpts_limit=self.num_cpts_limit, timeout=self.timeout,
             min_event_obs=self.min_event_obs)
         res = engine.run_host(batcher, params)
+        # the four datasets of every read as gzip chunks, straight from the pinned result arrays (libnrqio threads):
+        # no per-read event tables are built on this side, and the I/O processes neither deflate nor see numpy arrays
+        chunks = off = ln = None
+        if self.in_place:
+            from . import _libio
+            chunks, off, ln = _libio.pack_corrected(res.c_batch, res.c_results, len(ready))
         writes, writers = [], []
         for r, pr in enumerate(ready):
             pr.raw = None
@@ -258,17 +305,17 @@ class BatchPipeline(object):
                 sv = res.scale_values_of(r)
                 if norm_type != 'median':
                     sv = (pr.given[0], pr.given[1], sv[2], sv[3])
-                events = res.events_of(r)
+                packed = (int(res.n_bases[r]), len(pr.rows[0]), len(pr.starts)) + tuple(
+                    chunks[off[4 * r + j]:off[4 * r + j] + ln[4 * r + j]].tobytes() for j in range(4))
                 writes.append((
-                    pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, res.new_segs_of(r),
-                    events['base'].tobytes().decode(), pr.rows, pr.starts, None,
+                    pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, packed,
                     nh.scaleValues(*sv), self.corrected_group, pr.read_info.Subgroup, norm_type,
-                    self.outlier_thresh, self.compute_sd, events))
+                    self.outlier_thresh))
                 writers.append(pr)
             except Exception as e:  # noqa: BLE001
                 failed.append((str(e), pr))
         if writes:
-            self._writing.append((writers, fast5_jobs.start_jobs(fast5_jobs.write_job, writes),
+            self._writing.append((writers, fast5_jobs.start_jobs(fast5_jobs.write_packed_job, writes),
                                   set(pr.fast5_fn for pr in writers)))
         return failed
 
@@ -281,12 +328,20 @@ class BatchPipeline(object):
         return failed
 
     def _advance(self):
-        """push the batch whose reads are in flight through the device"""
+        """push the batch whose reads are in flight through the device.  An infrastructure failure (device error,
+        I/O pool failure) fails exactly the reads of THAT batch, as the worker's blanket except does for one read
+        (:434-438); the batch whose file reads have just been started is not touched by it."""
         failed = []
         if self._reading is not None:
             pending, loaded = self._reading
             self._reading = None
-            failed += self._process(pending, list(loaded))
+            try:
+                got = self._process(pending, list(loaded))
+                failed += got
+            except Exception as e:  # noqa: BLE001
+                # reads of this batch whose write-backs were already queued are reported by _collect_writes
+                queued = set(id(pr) for writers, _, _ in self._writing for pr in writers)
+                failed += [(str(e), pr) for pr in pending if id(pr) not in queued]
         return failed
 
     def feed(self, pending):
@@ -387,16 +442,15 @@ def resquiggle_worker(
         carry = carry_next
         if not pending:
             continue
+        # device / pool failures are turned into per-read failures of the batch they hit inside the pipeline
+        # (BatchPipeline._advance); what can still raise here is starting the file reads of `pending` itself
         try:
             failed = pipe.feed(pending)
-        except Exception as e:  # noqa: BLE001 -- infrastructure failure: every read of the batch fails
+        except Exception as e:  # noqa: BLE001
             failed = [(str(e), pr) for pr in pending]
         for text, pr in failed:
             failed_reads_q.put((text, pr.read_info.Subgroup + ' :: ' + pr.fast5_fn))
-    try:
-        failed = pipe.drain()
-    except Exception as e:  # noqa: BLE001
-        failed = [(str(e), pr) for pr in pending]
+    failed = pipe.drain()
     for text, pr in failed:
         failed_reads_q.put((text, pr.read_info.Subgroup + ' :: ' + pr.fast5_fn))
     return

@@ -375,7 +375,7 @@ def write_basecalled_fast5_job(job):
     grp.attrs['nanoraw_version'] = '0.5'
     grp.attrs['basecall_group'] = 'Basecall_1D_000'
     f.close()
-    return os.path.getsize(fn)
+    return os.path.getsize(fn) if os.path.exists(fn) else 0  # (mem:// names have no size)
 
 
 def drop_corrected_job(job):

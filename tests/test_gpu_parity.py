@@ -187,6 +187,68 @@ SEEDED = {
 }
 
 
+def assert_same_results(a, b, n_reads):
+    assert np.array_equal(a.status, b.status) and np.array_equal(a.n_bases, b.n_bases)
+    assert np.array_equal(a.n_indels, b.n_indels) and np.array_equal(a.region_samples, b.region_samples)
+    assert np.array_equal(a.scale_values, b.scale_values, equal_nan=True)
+    for r in range(n_reads):
+        if a.ok(r):
+            assert np.array_equal(a.new_segs_of(r), b.new_segs_of(r)), r
+            assert np.array_equal(a.events_of(r), b.events_of(r)), r
+
+
+@pytest.mark.parametrize('name', ['standard_10kb', 'indel_dense', 'low_dwell', 'tiny_batch'])
+def test_speculative_search_changes_nothing(engine, name):
+    """nrq_resegment runs the first change-point search of every indel group ahead of the read-by-read walk
+    (k_speculate, one region per thread); debug bit 2 turns that off.  Everything must come out the same either
+    way, and as in the oracle"""
+    from nanoraw_b200.engine import ResquiggleParams
+    genome = synth.make_genome(1_000_000, seed=9)
+    if name == 'tiny_batch':
+        reads = synth.make_reads(3, synth.SynthConfig(span_mean=150, span_sd=30, seed_base=71000), genome=genome)
+    else:
+        cfg, _ = SEEDED[name]
+        reads = synth.make_reads(12, cfg, genome=genome)
+    batch = ReadBatch.from_reads(reads)
+    on = engine.run(batch, ResquiggleParams())
+    off = engine.run(batch, ResquiggleParams(debug_flags=4))
+    assert_same_results(on, off, len(reads))
+    for r in (0, len(reads) - 1):
+        out = orc.resquiggle_read(reads[r].raw, reads[r].read_start_rel_to_raw, reads[r].starts,
+                                  reads[r].read_align.decode(), reads[r].genome_align.decode())
+        assert on.ok(r) and np.array_equal(on.new_segs_of(r), out['new_segs'])
+
+
+def test_speculative_search_at_the_edges_of_the_raw_array(engine):
+    """k_speculate reads DAC codes as whole 16-byte words: regions that begin at the first sample of the raw
+    array or end at its last one, and a raw array that starts off a 16-byte boundary, take the sample-by-sample
+    path for the words that stick out"""
+    import torch
+    from nanoraw_b200.engine import DeviceBatch, ResquiggleParams
+    rng = np.random.default_rng(7)
+    reads = []
+    for k in range(12):
+        rd = handmade_read(['MI', 'MMD'] * 6, 100 + k, dwell=10, lead=1 + k % 3, tail=1 + k % 2)
+        n = int(rd.starts[-1])
+        rd.raw = rd.raw[25:25 + n].copy()      # no samples before or after the read
+        rd.read_start_rel_to_raw = 0
+        reads.append(rd)
+    batch = ReadBatch.from_reads(reads)
+    want = engine.run_via_torch(batch, ResquiggleParams(debug_flags=4))
+    got = engine.run_via_torch(batch, ResquiggleParams())
+    assert_same_results(got, want, len(reads))
+    db = engine.upload(batch)
+    for shift in (1, 3, 7):
+        t = dict(db.t)
+        buf = torch.zeros(db.t['raw'].numel() + 16, dtype=torch.int16, device=db.device)
+        buf[shift:shift + db.t['raw'].numel()] = db.t['raw']
+        t['raw'] = buf[shift:shift + db.t['raw'].numel()]
+        assert t['raw'].data_ptr() % 16 == 2 * shift
+        moved = DeviceBatch.from_tensors(t, db.n_reads, db.total_align, db.device, host=db.host)
+        res = engine.download(moved, engine.run_device(moved, ResquiggleParams()))
+        assert_same_results(res, want, len(reads))
+
+
 @pytest.mark.parametrize('exact_stats', [False, True])
 @pytest.mark.parametrize('name', list(SEEDED))
 def test_seeded_reads_against_oracle(engine, name, exact_stats):
