@@ -523,11 +523,12 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
         t = pinned(getattr(host_batch, f))
         h2d += t.numel() * t.element_size()
         setattr(hb, f, t.data_ptr())
-    # what resquiggle_read hands to the FAST5 writer: scale values + the event table (+ status); new_segs is
-    # start/length again and region_samples is an accounting aid, so neither is copied back
-    outs = {'status': (R, np.int32), 'n_bases': (R, np.int32), 'n_indels': (R, np.int32),
+    # what resquiggle_read hands to the FAST5 writer: scale values + the event table (+ status).  new_segs and the
+    # `start` column are the running sum of `length` (nrqio_pack_corrected rebuilds start on the host), n_indels and
+    # region_samples are accounting aids: none of them is copied back
+    outs = {'status': (R, np.int32), 'n_bases': (R, np.int32),
             'scale_values': (4 * R, np.float64),
-            'norm_mean': (A, np.float64), 'norm_stdev': (A, np.float64), 'ev_start': (A, np.uint32),
+            'norm_mean': (A, np.float64), 'norm_stdev': (A, np.float64),
             'ev_length': (A, np.uint32), 'ev_base': (A, np.uint8)}
     # two sets of host result buffers: step i + 1 is submitted (nrq_resquiggle_batch_host_submit) while step i is
     # still coming back, as a worker that keeps reads coming does, so the copy / kernel pipeline never drains

@@ -36,12 +36,83 @@ uint32_t nrqio_adler32(const uint8_t* src, int64_t n);
  * for reads first .. first + count - 1 of a batch whose arrays are all in HOST memory (b: inputs, res: what
  * nrq_resquiggle_batch_host returned).  chunk_off and chunk_len have 4 * count entries each: chunk j of read
  * first + i is out[chunk_off[4 i + j] .. + chunk_len[4 i + j]) (chunks do not overlap; there may be gaps between
- * them).  Reads whose status is not NRQ_ST_OK get four empty chunks.  n_threads <= 1: in the calling thread.
+ * them).  Reads whose status is not NRQ_ST_OK get four empty chunks.  res->ev_start may be NULL (not copied back
+ * from the device): `start` is then the running sum of `length` from starts[0].  n_threads <= 1: in the calling
+ * thread.
  * Returns 0, or -1 (bad argument / out smaller than nrqio_pack_corrected_bound says). */
 int64_t nrqio_pack_corrected_bound(const nrq_batch* b, const nrq_results* res, int32_t first, int32_t count);
 int nrqio_pack_corrected(const nrq_batch* b, const nrq_results* res, int32_t first, int32_t count,
                          int32_t n_threads, uint8_t* out, int64_t out_cap, int64_t* chunk_off,
                          int64_t* chunk_len);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Front end: what turns a basecalled read and its SAM record into the inputs of the
+ * hot path.  Integer / byte work, one read at a time or a whole batch on threads, written into the CSR arrays of
+ * nrq_batch directly.  Per-read outcomes are status codes; nrqio_fe_message gives the reference's message.
+ * ------------------------------------------------------------------------------------------------------------ */
+enum {
+  NRQIO_FE_OK = 0,
+  NRQIO_FE_EVENTS_BEFORE_RAW = 1,  /* resquiggle.py:856-858 */
+  NRQIO_FE_TOO_FEW_SEGMENTS = 2,   /* resquiggle.py:891-894 */
+  NRQIO_FE_ZERO_LENGTH = 3,        /* resquiggle.py:895-898 */
+  NRQIO_FE_ALL_STAYS = 4,          /* resquiggle.py:774-777 */
+  NRQIO_FE_BAD_CIGAR = 5,          /* resquiggle.py:586-588 */
+  NRQIO_FE_SEQ_CIGAR_DISAGREE = 6, /* resquiggle.py:639-641 */
+  NRQIO_FE_CAPACITY = 7,           /* an output array of the caller is too small */
+  NRQIO_FE_BAD_INPUT = 8
+};
+const char* nrqio_fe_message(int32_t status);
+
+/* Basecall events -> starts_rel_to_read, basecalls, read_start_rel_to_raw: the arithmetic of get_read_data
+ * (resquiggle.py:848-898) followed by fix_stay_states (:767-805).
+ *   ev_start / ev_length   the Events columns `start`, `length` (seconds), float32 (is_f32 != 0) or float64
+ *   model_state            n_events x state_len bytes (the k-mer of each event; its third character is the call)
+ *   move                   n_events integers of move_size bytes (1, 2, 4, 8; signed)
+ *   albacore_after_1_0     group attribute version > "1.0": boundaries from `length` (:872-877), else from `start`
+ *   sampling_rate          channel_info.sampling_rate (an integer, nanoraw_helper.py:164)
+ *   raw_start_time         /Raw/Reads/<read>.attrs['start_time']
+ * Outputs: starts[*n_starts] (capacity n_events + 1), bases[*n_starts - 1] (capacity n_events), *read_start. */
+int nrqio_events_to_starts(const void* ev_start, int32_t start_is_f32, const void* ev_length, int32_t length_is_f32,
+                           const uint8_t* model_state, int32_t state_len, const void* move, int32_t move_size,
+                           int64_t n_events, int32_t albacore_after_1_0, int64_t sampling_rate,
+                           uint64_t raw_start_time, int64_t* starts, uint8_t* bases, int64_t* n_starts,
+                           int64_t* read_start);
+
+/* One SAM record -> the two alignment rows in read orientation (parse_sam_record, resquiggle.py:583-660):
+ * CIGAR (\d+)([MIDNSHP=X]), flag & 0x10 = reverse strand (CIGAR reversed, sequences reverse-complemented), hard /
+ * soft clips counted and trimmed, leading / trailing non-match operations stripped (with the reference's
+ * cigar[0][0] quirk at :636), '-' for gaps.  contig: the reference sequence named by the record (rName).
+ * read_row / genome_row: capacity row_cap each (the sum of all CIGAR lengths always suffices).
+ * clip[2]: bases clipped from the read's start / end; tallies[4]: insertions, deletions, matches, mismatches as
+ * fix_all_clipped_bases counts them (:476-485).  Genome position of the alignment = pos - 1 (:658). */
+int nrqio_sam_to_rows(const char* cigar, int32_t flag, int64_t pos, const char* seq, int64_t seq_len,
+                      const char* contig, int64_t contig_len, char* read_row, char* genome_row, int64_t row_cap,
+                      int64_t* n_cols, int64_t* clip, int64_t* tallies);
+
+/* fix_raw_starts_for_clipped_bases (resquiggle.py:447-460), in place */
+int nrqio_clip_starts(int64_t* starts, int64_t* n_starts, int64_t* read_start, int64_t clip_start, int64_t clip_end);
+
+/* A batch of reads, SAM records + stay-free starts in, CSR arrays of nrq_batch out (on n_threads threads). */
+typedef struct nrqio_fe_read {
+  const char* cigar;
+  int32_t flag;
+  int64_t pos;
+  const char* seq;
+  int64_t seq_len;
+  const char* contig;
+  int64_t contig_len;
+  const int64_t* starts;  /* starts_rel_to_read after fix_stay_states, n_starts entries */
+  int64_t n_starts;
+  int64_t read_start;     /* read_start_rel_to_raw after fix_stay_states */
+} nrqio_fe_read;
+/* Fills, for read i: status[i]; read_start[i]; starts[starts_off[i] .. starts_off[i + 1]) (int32, clip-fixed);
+ * read_align / genome_align[align_off[i] .. align_off[i + 1]); clip[2 i ..]; tallies[4 i ..].  starts_off and
+ * align_off get n_reads + 1 entries; a read that fails gets empty ranges.  Returns 0, or NRQIO_FE_CAPACITY if
+ * starts_cap / align_cap are too small (nothing useful written). */
+int nrqio_frontend_batch(const nrqio_fe_read* reads, int32_t n_reads, int32_t n_threads, int32_t* status,
+                         int32_t* read_start, int32_t* starts, int64_t starts_cap, int64_t* starts_off,
+                         uint8_t* read_align, uint8_t* genome_align, int64_t align_cap, int64_t* align_off,
+                         int64_t* clip, int64_t* tallies);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,28 @@ SYMBOLS = {
                                        C.c_int32, _P, C.c_int64, _P, _P]),
 }
 
+SYMBOLS.update({
+    'nrqio_fe_message': (C.c_char_p, [C.c_int32]),
+    'nrqio_events_to_starts': (C.c_int, [_P, C.c_int32, _P, C.c_int32, _P, C.c_int32, _P, C.c_int32, C.c_int64,
+                                         C.c_int32, C.c_int64, C.c_uint64, _P, _P, _P, _P]),
+    'nrqio_sam_to_rows': (C.c_int, [C.c_char_p, C.c_int32, C.c_int64, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64,
+                                    _P, _P, C.c_int64, _P, _P, _P]),
+    'nrqio_clip_starts': (C.c_int, [_P, _P, _P, C.c_int64, C.c_int64]),
+    'nrqio_frontend_batch': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P, C.c_int64, _P, _P, _P, C.c_int64, _P,
+                                       _P, _P]),
+})
+
+FE_OK, FE_EVENTS_BEFORE_RAW, FE_TOO_FEW_SEGMENTS, FE_ZERO_LENGTH, FE_ALL_STAYS, FE_BAD_CIGAR, \
+    FE_SEQ_CIGAR_DISAGREE, FE_CAPACITY, FE_BAD_INPUT = range(9)
+
+
+class FeRead(C.Structure):
+    """nrqio_fe_read"""
+    _fields_ = [('cigar', C.c_char_p), ('flag', C.c_int32), ('pos', C.c_int64), ('seq', C.c_char_p),
+                ('seq_len', C.c_int64), ('contig', C.c_char_p), ('contig_len', C.c_int64), ('starts', _P),
+                ('n_starts', C.c_int64), ('read_start', C.c_int64)]
+
+
 _io = None
 
 
@@ -80,3 +102,56 @@ def pack_corrected(c_batch, c_results, n_reads, threads=None):
     if rc != 0:
         raise _lib.NrqError('nrqio_pack_corrected failed')
     return out, off, ln
+
+
+def fe_message(status):
+    return load().nrqio_fe_message(int(status)).decode()
+
+
+def events_to_starts(events, albacore_after_1_0, sampling_rate, raw_start_time):
+    """nrqio_events_to_starts on an Events table -> (status, starts int64[], bases bytes, read_start)"""
+    lib = load()
+    n = len(events)
+    cols = {}
+    for name in ('start', 'length'):
+        c = np.ascontiguousarray(events[name])
+        if c.dtype not in (np.float32, np.float64):
+            c = c.astype(np.float64)
+        cols[name] = c
+    states = np.ascontiguousarray(events['model_state'])
+    if states.dtype.kind != 'S':
+        states = states.astype('S')
+    move = np.ascontiguousarray(events['move'])
+    if move.dtype.kind not in 'iu' or move.dtype.kind == 'u':
+        move = move.astype(np.int64)
+    starts = np.empty(n + 1, dtype=np.int64)
+    bases = np.empty(max(n, 1), dtype=np.uint8)
+    n_starts = C.c_int64(0)
+    read_start = C.c_int64(0)
+    st = lib.nrqio_events_to_starts(
+        cols['start'].ctypes.data, int(cols['start'].dtype == np.float32),
+        cols['length'].ctypes.data, int(cols['length'].dtype == np.float32),
+        states.ctypes.data, states.dtype.itemsize, move.ctypes.data, move.dtype.itemsize, n,
+        int(bool(albacore_after_1_0)), int(sampling_rate), int(raw_start_time),
+        starts.ctypes.data, bases.ctypes.data, C.byref(n_starts), C.byref(read_start))
+    k = n_starts.value
+    return st, starts[:k].copy(), bases[:max(k - 1, 0)].tobytes(), read_start.value
+
+
+def sam_to_rows(cigar, flag, pos, seq, contig):
+    """nrqio_sam_to_rows -> (status, read_row bytes, genome_row bytes, (clip_start, clip_end), tallies[4])"""
+    lib = load()
+    cigar_b = cigar.encode() if isinstance(cigar, str) else cigar
+    seq_b = seq.encode() if isinstance(seq, str) else seq
+    contig_b = contig.encode() if isinstance(contig, str) else contig
+    cap = len(seq_b) + sum(int(x) for x in __import__('re').findall(rb'(\d+)[MIDNSHP=X]', cigar_b)) + 16
+    rr = np.empty(cap, dtype=np.uint8)
+    gr = np.empty(cap, dtype=np.uint8)
+    n_cols = C.c_int64(0)
+    clip = np.zeros(2, dtype=np.int64)
+    tallies = np.zeros(4, dtype=np.int64)
+    st = lib.nrqio_sam_to_rows(cigar_b, int(flag), int(pos), seq_b, len(seq_b), contig_b, len(contig_b),
+                               rr.ctypes.data, gr.ctypes.data, cap, C.byref(n_cols), clip.ctypes.data,
+                               tallies.ctypes.data)
+    k = n_cols.value
+    return st, rr[:k].tobytes(), gr[:k].tobytes(), (int(clip[0]), int(clip[1])), tallies

@@ -189,10 +189,10 @@ int nrq_find_indels(const nrq_batch* b, int32_t* status, int32_t* n_indels, int3
   if (indels) {
     if (wide)
       nrq::k_align_fill<true><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(
-          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base, status);
+          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base);
     else
       nrq::k_align_fill<false><<<grid, nrq::kWarpsPerCta * 32, 0, s>>>(
-          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base, status);
+          *b, status, indel_off, reinterpret_cast<int4*>(indels), indel_capacity, ev_base);
     NRQ_CHECK_LAUNCH("k_align_fill");
   }
   return 0;
@@ -488,10 +488,14 @@ int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, cons
   const int R = b->n_reads;
   cudaError_t ce = cudaSetDevice(h->device);
   if (ce != cudaSuccess) return fail("cudaSetDevice", ce);
-  const int64_t id = h->next_ticket++;
+  const int64_t id = h->next_ticket;
   cudaEvent_t& done_ev = h->ticket[id % kTickets];
+  // the slot still belongs to ticket id - kTickets: a 17th batch is refused while that one is in flight
+  if (done_ev && id >= kTickets && cudaEventQuery(done_ev) == cudaErrorNotReady)
+    return fail("nrq_resquiggle_batch_host_submit: 16 batches are outstanding already (wait for the oldest first)");
   if (!done_ev && cudaEventCreateWithFlags(&done_ev, cudaEventDisableTiming) != cudaSuccess)
     return fail("nrq_resquiggle_batch_host_submit: event creation failed");
+  ++h->next_ticket;
   if (R == 0) {
     cudaEventRecord(done_ev, h->d2h);
     return id;
@@ -630,7 +634,8 @@ int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, cons
 int nrq_resquiggle_batch_host_wait(nrq_handle* h, int64_t ticket) {
   if (!h) return fail("handle is NULL");
   if (ticket < 0 || ticket >= h->next_ticket) return fail("nrq_resquiggle_batch_host_wait: unknown ticket");
-  if (h->next_ticket - ticket > kTickets) return 0;  // its event has been reused by a later batch, which queued behind it and is waited for by its own ticket
+  // An older ticket's event slot has been taken over by a later batch; that batch was recorded later on the same
+  // FIFO download stream, so waiting for it covers the older one as well.
   cudaError_t ce = cudaSetDevice(h->device);
   if (ce == cudaSuccess) ce = cudaEventSynchronize(h->ticket[ticket % kTickets]);
   if (ce != cudaSuccess) return fail("nrq_resquiggle_batch_host_wait", ce);

@@ -181,9 +181,8 @@ __device__ __forceinline__ int pymod(int a, int n) {
 
 template <bool WIDE>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
-k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __restrict__ indel_off,
-             int4* __restrict__ indels, int64_t indel_capacity, uint8_t* __restrict__ ev_base,
-             int32_t* __restrict__ status_out) {
+k_align_fill(nrq_batch b, int32_t* status, const int64_t* __restrict__ indel_off,
+             int4* __restrict__ indels, int64_t indel_capacity, uint8_t* __restrict__ ev_base) {
   // lane-0 broadcast: marks r (and what is loaded through it) warp-uniform for the compiler
   int r = blockIdx.x * kWarpsPerCta + __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
   if (r >= b.n_reads || status[r] != NRQ_ST_OK) return;
@@ -198,7 +197,7 @@ k_align_fill(nrq_batch b, const int32_t* __restrict__ status, const int64_t* __r
   int4* out = indels + indel_off[r];
   int n_ind = (int)(indel_off[r + 1] - indel_off[r]);
   if (indel_off[r + 1] > indel_capacity) {  // caller's indel buffer is too small for this read
-    if (lane == 0) status_out[r] = NRQ_ST_WORKSPACE;
+    if (lane == 0) status[r] = NRQ_ST_WORKSPACE;
     return;
   }
   uint8_t* bases = ev_base ? ev_base + a0 : nullptr;  // align_seq: genome row without gaps (resquiggle.py:384)

@@ -134,6 +134,70 @@ __device__ __forceinline__ unsigned long long block_bisect(const int16_t* sig, i
   return klo;
 }
 
+#ifndef NRQ_NORM_BULK
+#define NRQ_NORM_BULK 0
+#endif
+#if NRQ_NORM_BULK
+// Experiment (profiles/README.md, "bulk-async staging"): the read streamed into shared memory by one thread with
+// 1-D bulk copies (cp.async.bulk + mbarrier complete_tx, the TMA engine's non-tensor form) in a two-deep ring of
+// kBulkTile bytes, the other threads taking their samples from there.  The loads leave the issue slots (one
+// UBLKCP per tile instead of a LDG.128 per eight samples and thread); the shared-memory atomics stay.
+constexpr int kBulkTile = 4096;  // bytes per stage = 2048 samples = 8 samples per thread
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// visit every sample once: head and tail (to 16-byte alignment / tile size) by plain loads, the middle through the ring
+template <class F>
+__device__ __forceinline__ void for_each_sample_bulk(const int16_t* __restrict__ sig, int n, int4* ring,
+                                                     unsigned long long* bars, F f) {
+  const int tid = threadIdx.x;
+  int head = (int)(((16u - (unsigned)((uintptr_t)sig & 15u)) & 15u) >> 1);
+  if (head > n) head = n;
+  for (int i = tid; i < head; i += kNormThreads) f((int)sig[i]);
+  const int16_t* mid = sig + head;
+  const int tiles = (n - head) / (kBulkTile / 2);
+  constexpr int kTileVec = kBulkTile / 16;  // int4 per tile
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bars + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    if (tiles > 0) bulk_load(ring, mid, kBulkTile, bars);
+    if (tiles > 1) bulk_load(ring + kTileVec, mid + kBulkTile / 2, kBulkTile, bars + 1);
+  }
+  for (int t = 0; t < tiles; ++t) {
+    const int s = t & 1;
+    bar_wait(bars + s, (unsigned)((t >> 1) & 1));
+    for (int i = tid; i < kTileVec; i += kNormThreads) {
+      const int4 q = ring[s * kTileVec + i];
+      f((int)(short)(q.x & 0xffff)); f((int)(short)(q.x >> 16));
+      f((int)(short)(q.y & 0xffff)); f((int)(short)(q.y >> 16));
+      f((int)(short)(q.z & 0xffff)); f((int)(short)(q.z >> 16));
+      f((int)(short)(q.w & 0xffff)); f((int)(short)(q.w >> 16));
+    }
+    __syncthreads();  // everybody is done with stage s
+    if (tid == 0 && t + 2 < tiles) bulk_load(ring + s * kTileVec, mid + (size_t)(t + 2) * (kBulkTile / 2), kBulkTile, bars + s);
+  }
+  for (int i = head + tiles * (kBulkTile / 2) + tid; i < n; i += kNormThreads) f((int)sig[i]);
+  __syncthreads();
+  if (tid == 0) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(bars)));
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_addr(bars + 1)));
+  }
+}
+#endif
+
 __device__ __forceinline__ unsigned long long dbits(double x) {
   return (unsigned long long)__double_as_longlong(x);
 }
@@ -149,6 +213,10 @@ k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __
   __shared__ int sh_res[2];
   __shared__ double sh_d[4];
   __shared__ int sh_flag;
+#if NRQ_NORM_BULK
+  __shared__ __align__(128) int4 bulk_ring[2 * kBulkTile / 16];
+  __shared__ __align__(8) unsigned long long bulk_bars[2];
+#endif
 
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
@@ -189,10 +257,15 @@ k_norm_stats(nrq_batch b, nrq_params p, int32_t* __restrict__ status, double* __
     // (left to the compiler it is re-derived per sample, and the two-sided test costs four branch instructions)
     unsigned hist_sa = (unsigned)__cvta_generic_to_shared(hist_all);
     asm volatile("" : "+r"(hist_sa));
-    for_each_sample(sig, n, [&](int v) {
+    auto count_sample = [&](int v) {
       const int slot = min(max(v - lo_w, -1), kWin) + 1;
       asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_sa + 4u * (unsigned)slot) : "memory");
-    });
+    };
+#if NRQ_NORM_BULK
+    for_each_sample_bulk(sig, n, bulk_ring, bulk_bars, count_sample);
+#else
+    for_each_sample(sig, n, count_sample);
+#endif
     __syncthreads();
     below = hist[-1];
     above = hist[kWin];

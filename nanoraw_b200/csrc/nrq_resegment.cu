@@ -284,17 +284,18 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
 
 // extend_for_cpts (:256-276) for a group whose extend_group result is already known, preceded by the merge
 // loop of extend_and_join (:220-225)
-// known_none: K2a searched exactly this (start, stop, K) and found None; only honoured if no merge happens first
+// known_none: K2a searched exactly this (start, stop, K) and that many of its retries, and found None every time;
+// honoured only up to the first merge with a finished group (what follows a merge is a different search)
 __device__ __forceinline__ int search_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop,
-                                            int K, int t_start, int t_stop, bool known_none = false) {
-  if (start <= c.top_stop) known_none = false;
+                                            int K, int t_start, int t_stop, int known_none = 0) {
+  if (start <= c.top_stop) known_none = 0;
   int st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
   if (st != NRQ_ST_OK) return st;
   for (;;) {
     int res = 0;
-    if (known_none) {
+    if (known_none > 0) {
       if (c.limit >= 0 && K > c.limit) return NRQ_ST_CPTS_LIMIT;
-      known_none = false;
+      --known_none;
     } else {
       res = get_cpts(c, t_start, t_stop, K, start + c.ind[lo].w + 1);
     }
@@ -306,6 +307,7 @@ __device__ __forceinline__ int search_group(SegCtx& c, int& lo, int hi, int& max
     stop = min(c.last, stop + 1);
     t_start = c.t[start];
     t_stop = c.t[stop];
+    if (start <= c.top_stop) known_none = 0;
     st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
     if (st != NRQ_ST_OK) return st;
   }
@@ -464,10 +466,16 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       if (K < 0 || K >= (1 << kPlanKBits)) { st = kPlanGeneric; K = 0; }
       c.groups[k + lane] = make_int4(start, stop, K | ((e - lane) << kPlanKBits) | (st << (kPlanKBits + 5)), gmax);
       p_start = start; p_stop = stop; p_K = K;
-      // K2a's result counts only if it searched this very plan
+      // K2a's result counts only if it started from this very plan
       if (st == NRQ_ST_OK && K >= 1 && K <= kSpecMaxK && stop - start <= 255 && e - lane <= kSpecMaxLen) {
         sp_found = spw.x == spec_word(kSpecFound, K, start, stop);
         sp_none = spw.x == spec_word(kSpecNone, K, start, stop);
+      }
+      if (sp_found) {  // where its retries (:262-266) ended: one base more on either side per retry
+        const int nret = spec_retries(spw.y);
+        p_K = K + min(nret, start) + min(nret, c.last - stop);
+        p_start = max(0, start - nret);
+        p_stop = min(c.last, stop + nret);
       }
     }
     const unsigned found_mask = __ballot_sync(kFull, sp_found), none_mask = __ballot_sync(kFull, sp_none);
@@ -494,7 +502,7 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
           c.groups[c.ng + __popc(prefix & ((1u << lane) - 1u))] = make_int4(p_start, p_stop, k + lane, gmax);
           const int t0 = c.t[p_start];
           int32_t* o = c.out + p_start + my.w + 1;
-          const unsigned char* src = c.cpt_bytes + spw.y;
+          const unsigned char* src = c.cpt_bytes + spec_offset(spw.y);
           for (int i = 0; i < p_K; ++i) o[i] = t0 + (int)src[i];
         }
         const int last_lane = 31 - __clz(prefix);
@@ -522,15 +530,22 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
         break;
       }
       if (st != NRQ_ST_OK) return st;
-      const int cpt_off = __shfl_sync(kFull, spw.y, s);
-      if (((found_mask >> s) & 1u) && start > c.top_stop) {  // searched by K2a, and no finished group in the way
-        const int K = rec.z & ((1 << kPlanKBits) - 1);
+      const int sp_y = __shfl_sync(kFull, spw.y, s);
+      const int f_start = __shfl_sync(kFull, p_start, s), f_stop = __shfl_sync(kFull, p_stop, s);
+      const int f_K = __shfl_sync(kFull, p_K, s);
+      const bool found = (found_mask >> s) & 1u;
+      if (found && f_start > c.top_stop) {  // searched by K2a to the end, and no finished group in the way
+        start = f_start;
+        stop = f_stop;
         const int t0 = c.t[start];
         int32_t* o = c.out + start + c.ind[lo].w + 1;
-        for (int i = lane; i < K; i += 32) o[i] = t0 + (int)c.cpt_bytes[cpt_off + i];
+        const unsigned char* src = c.cpt_bytes + spec_offset(sp_y);
+        for (int i = lane; i < f_K; i += 32) o[i] = t0 + (int)src[i];
       } else {
+        // searches K2a is known to have lost: all of a chain that ended in None, the retries before a find
+        const int known = found ? spec_retries(sp_y) : (((none_mask >> s) & 1u) ? spec_retries(sp_y) + 1 : 0);
         st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop],
-                          (none_mask >> s) & 1u);
+                          known);
         if (st != NRQ_ST_OK) return st;
       }
       if (hi + 1 < c.n_ind) {

@@ -48,11 +48,24 @@ constexpr int kSpecMaxK = 61;
 constexpr int kSpecMaxLen = 30;                // indels after the head: K2b plans 32-indel windows
 constexpr int kSpecM = 4;                      // min_seg_len this kernel is written for
 
-// spec entry of a group head: .x = what was searched (so that K2b can tell its own plan is the same one) and the
-// outcome, .y = where the found change-points lie in the read's byte scratch (one byte each: offset from the region's
-// first sample).  Speculated results never go to new_segs directly: the regions of neighbouring speculated groups may
+// spec entry of a group head: .x = the group's first plan (so that K2b can tell its own plan is the same one) and
+// the outcome, .y = how many retries (:262-266: one base more on either side, K grown to match) came before it and
+// where the found change-points lie in the read's byte scratch (one byte each: offset from the region's first
+// sample).  A retry chain is followed as long as nothing only the walk can know gets in the way; it assumes that no
+// finished group is run into (:267-272), which K2b checks against the final region before it takes the result.  Speculated results never go to new_segs directly: the regions of neighbouring speculated groups may
 // overlap, and a group K2b ends up merging would otherwise leave its marks in a neighbour's slots.
 constexpr int kSpecFound = 1, kSpecNone = 2;
+// Longest chain of retries followed here.  0: a search that comes back None is left to the walk.  Measured (r2e,
+// profiles/README.md): with chains followed to the end (24) the walk gets 14 % faster and this kernel 3.3 times
+// slower -- a round of retries is a tenth of the tasks of the round before, so most warps of the CTA wait at its
+// barriers.  The mechanism stays for a pool that holds the tasks of several reads.
+#ifndef NRQ_SPEC_RETRY
+#define NRQ_SPEC_RETRY 0
+#endif
+constexpr int kSpecMaxRetry = NRQ_SPEC_RETRY;
+// .y of an entry: byte offset of the change-points (24 bits) | retries before the outcome << 24
+__host__ __device__ __forceinline__ int spec_retries(int y) { return (int)((unsigned)y >> 24); }
+__host__ __device__ __forceinline__ int spec_offset(int y) { return y & 0xffffff; }
 constexpr int kSpecCptBytesPerIndel = 8;  // byte scratch per read: this many bytes per indel
 __host__ __device__ __forceinline__ int spec_word(int flag, int K, int start, int stop) {
   return flag | (K << 2) | ((stop - start) << 8) | ((start & 0xffff) << 16);
@@ -63,6 +76,8 @@ struct SpecTask {
   unsigned pk;  // samples (8 bits) | K << 8 (6) | indels after the head << 14 (5) | (stop - start) << 19 (8)
   int start;    // group start (read base index)
   int lo;       // the group's first indel
+  int word0;    // spec_word(0, ...) of the group's first plan
+  int nret;     // retries that led to this task
 };
 
 struct SpecSm {
@@ -76,7 +91,7 @@ struct SpecSm {
   int zs[kSpecThreads];  // sum of diffs up to and including this indel
   unsigned heads[kSpecWarps];
   int wmax[kSpecWarps];
-  int n_tasks, cursor, read, cpt_alloc;
+  int n_tasks, cursor, read, cpt_alloc, n_retry;
 };
 
 // Sort bin of a task: tasks of one batch run in lock-step, so they should need the same number of selection rounds
@@ -105,17 +120,18 @@ __device__ __forceinline__ int4 spec_load_word(const int4* q, const int16_t* raw
 template <bool FULL>
 __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, int i0, int L, const int16_t* sig,
                                                const int16_t* raw_lo, const int16_t* raw_hi, const NormCoef& coef,
-                                               int lut_lo, int2* sp, unsigned char* cpt_bytes, int cpt_cap) {
+                                               int lut_lo, int2* sp, unsigned char* cpt_bytes, int cpt_cap,
+                                               const int32_t* t, int last, int limit, int nt) {
   const bool act = lane < L;
   SpecTask tk;
-  tk.t0 = 0; tk.pk = 0u; tk.start = 0; tk.lo = 0;
+  tk.t0 = 0; tk.pk = 0u; tk.start = 0; tk.lo = 0; tk.word0 = 0; tk.nret = 0;
   if (act) tk = sm.task[sm.order[i0 + lane]];
   const int n = (int)(tk.pk & 255u);
   const int K = (int)((tk.pk >> 8) & 63u);
   const int nrd = act ? n - 2 * kSpecM + 1 : 0;  // len(running_diffs)
   const int nb_max = ((int)__reduce_max_sync(kFull, (unsigned)nrd) + 7) >> 3;  // key blocks of the largest region
   const int nrd_max = 8 * nb_max;
-  const int nrd_min = (int)__reduce_min_sync(kFull, act ? (unsigned)nrd : (unsigned)nrd_max);
+  const int nb_own = (nrd + 7) >> 3;  // this lane's key blocks
   const int col = act ? lane : 0;
   long long* slab = sm.slab[warp];       // key i of this lane at slab[i * L + col], i < 8 nb_max
   long long* bmax = slab + nrd_max * L;  // largest key of block b at bmax[b * L + col]
@@ -123,8 +139,9 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
   __syncwarp();  // the previous batch's columns are laid out differently
 #pragma unroll
   for (int w = 0; w < 8; ++w) pick[w * 32 + lane] = 0u;
-  for (int j = nrd_min; j < nrd_max; ++j)
-    if (act && j >= nrd) slab[j * L + col] = -1ll;  // never a candidate
+  if (act) {  // the tail of the lane's last block is never a candidate
+    for (int j = nrd; j < 8 * nb_own; ++j) slab[j * L + col] = -1ll;
+  }
 
   // ---- cumulative sum and keys.  The lane reads whole 16-byte words; samples of the first word that lie before the
   // region count as +0.0 (cs stays +0.0, exactly), so that the position inside the word fixes which of the eight
@@ -141,6 +158,10 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[k] = 0.0;
     double acc = 0.0;
+    // every word of the lane's region starts its trip from HBM now (no register held for it); the loop below then
+    // finds them in L1
+    for (int it = 2; it < iters; ++it)
+      if (8 * it < nv) asm volatile("prefetch.global.L1 [%0];" ::"l"(wp + it));
     int4 nxt = make_int4(0, 0, 0, 0);
     if (nv > 0) nxt = spec_load_word(wp, raw_lo, raw_hi);
     int rel = -off;                                  // region index of the word's first sample
@@ -191,7 +212,8 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
     return v;
   };
   for (int b = 0; b < nb_max; ++b) {
-    const long long v = block_max(b);
+    long long v = -1ll;  // blocks beyond the lane's own region: nothing there
+    if (b < nb_own) v = block_max(b);
     if (act) bmax[b * L + col] = v;
   }
   const int Kmax = (int)__reduce_max_sync(kFull, (unsigned)K);
@@ -217,9 +239,9 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
 #pragma unroll
         for (int d = -kSpecM + 1; d <= kSpecM; ++d) {
           const int i = bi + d;
-          if ((unsigned)i < (unsigned)nrd_max) slab[i * L + col] = -1ll;
+          if ((unsigned)i < (unsigned)(8 * nb_own)) slab[i * L + col] = -1ll;
         }
-        const int b_lo = max(bi - kSpecM + 1, 0) >> 3, b_hi = min(bi + kSpecM, nrd_max - 1) >> 3;
+        const int b_lo = max(bi - kSpecM + 1, 0) >> 3, b_hi = min(bi + kSpecM, 8 * nb_own - 1) >> 3;
         bmax[b_lo * L + col] = block_max(b_lo);
         if (b_hi != b_lo) bmax[b_hi * L + col] = block_max(b_hi);
       }
@@ -227,15 +249,15 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
     if (!__any_sync(kFull, round + 1 < K && !fail)) break;
   }
 
-  // ---- sorted(cpt + min_seg_len) (:255) as byte offsets from the region's first sample, into the read's scratch
+  // ---- found: sorted(cpt + min_seg_len) (:255) as byte offsets from the region's first sample, into the read's
+  // scratch.  None: the retry of extend_for_cpts (:262-266) becomes a task of the next round.
   if (act) {
     const int start = tk.start, stop = start + (int)((tk.pk >> 19) & 255u);
-    int2 entry = make_int2(spec_word(kSpecNone, K, start, stop), 0);
+    int2 entry = make_int2(0, 0);  // "not speculated"
     if (!fail) {
       const int base = atomicAdd(&sm.cpt_alloc, K);
-      entry = make_int2(0, 0);  // no room left in the scratch: not speculated
-      if (base + K <= cpt_cap) {
-        entry = make_int2(spec_word(kSpecFound, K, start, stop), base);
+      if (base + K <= min(cpt_cap, 1 << 24)) {
+        entry = make_int2(tk.word0 | kSpecFound, base | (tk.nret << 24));
         unsigned char* o = cpt_bytes + base;
         int c = 0;
         for (int w = 0; w * 32 < nrd; ++w) {
@@ -247,8 +269,28 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
           }
         }
       }
+    } else {
+      bool again = tk.nret < kSpecMaxRetry && !(start == 0 && stop == last);
+      SpecTask nx = tk;
+      if (again) {
+        const int K2 = K + (start > 0) + (stop < last);
+        const int s2 = max(0, start - 1), e2 = min(last, stop + 1);
+        const int ts = t[s2], n2 = t[e2] - ts;
+        again = K2 <= kSpecMaxK && n2 <= kSpecMaxN && e2 - s2 <= 255 && (limit < 0 || K2 <= limit);
+        nx.t0 = ts;
+        nx.pk = (unsigned)n2 | ((unsigned)K2 << 8) | (tk.pk & (31u << 14)) | ((unsigned)(e2 - s2) << 19);
+        nx.start = s2;
+        nx.nret = tk.nret + 1;
+      }
+      if (again) {
+        const int slot = nt + atomicAdd(&sm.n_retry, 1);
+        again = slot < kSpecPool;
+        if (again) sm.task[slot] = nx;
+      }
+      if (again) entry.x = -1;  // outcome still to come
+      else entry = make_int2(tk.word0 | kSpecNone, tk.nret << 24);  // nret + 1 searches without merges: all None
     }
-    sp[tk.lo] = entry;
+    if (entry.x != -1) sp[tk.lo] = entry;
   }
 }
 
@@ -317,8 +359,10 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
       __syncthreads();
       const int nt_now = min(sm.n_tasks, kSpecPool);
       if ((!more && nt_now > 0) || nt_now > kSpecPool - 64) {
-        // ---- run the pool: counting sort by region size (largest first), then warps take batches
-        const int nt = nt_now;
+        // ---- run the pool: counting sort by cost, then warps take batches; searches that came back None leave their
+        // retry in the pool's tail, which is the pool of the next round
+        int nt = nt_now;
+        for (;;) {
         for (int k = tid; k < 256; k += kSpecThreads) sm.hist[k] = 0;
         __syncthreads();
         for (int i = tid; i < nt; i += kSpecThreads) atomicAdd(&sm.hist[spec_bin(sm.task[i].pk)], 1);
@@ -340,7 +384,7 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         __syncthreads();
         for (int i = tid; i < nt; i += kSpecThreads)
           sm.order[atomicAdd(&sm.hist[spec_bin(sm.task[i].pk)], 1)] = (unsigned short)i;
-        if (tid == 0) sm.cursor = 0;
+        if (tid == 0) { sm.cursor = 0; sm.n_retry = 0; }
         __syncthreads();
         for (;;) {
           // the next L tasks in sorted order: as many as the warp's slab holds (keys in blocks of 8 + a maximum per
@@ -366,11 +410,19 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
           }
           if (L == 0) break;
           if (lut_full)
-            spec_run_batch<true>(sm, warp, lane, i0, L, g.sig, raw_lo, raw_hi, coef, lut_lo, sp, cpt_bytes, cpt_cap);
+            spec_run_batch<true>(sm, warp, lane, i0, L, g.sig, raw_lo, raw_hi, coef, lut_lo, sp, cpt_bytes, cpt_cap,
+                                 t, last, p.num_cpts_limit, nt);
           else
-            spec_run_batch<false>(sm, warp, lane, i0, L, g.sig, raw_lo, raw_hi, coef, lut_lo, sp, cpt_bytes, cpt_cap);
+            spec_run_batch<false>(sm, warp, lane, i0, L, g.sig, raw_lo, raw_hi, coef, lut_lo, sp, cpt_bytes, cpt_cap,
+                                  t, last, p.num_cpts_limit, nt);
         }
         __syncthreads();
+        const int n_again = min(sm.n_retry, kSpecPool - nt);  // (one retry per task at most: n_again <= nt)
+        if (n_again <= 0) break;
+        for (int i = tid; i < n_again; i += kSpecThreads) sm.task[i] = sm.task[nt + i];
+        nt = n_again;
+        __syncthreads();
+        }
         if (tid == 0) sm.n_tasks = 0;
         __syncthreads();
       }
@@ -447,6 +499,8 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
             tk.pk = (unsigned)n | ((unsigned)K << 8) | ((unsigned)(e - tid) << 14) | ((unsigned)(stop - start) << 19);
             tk.start = start;
             tk.lo = idx;
+            tk.word0 = spec_word(0, K, start, stop);
+            tk.nret = 0;
             sm.task[slot] = tk;
           }
         }

@@ -248,10 +248,12 @@ class ResquiggleEngine(object):
         if h:
             self.lib.nrq_destroy(h)
 
-    def run_host(self, src, params):
+    def run_host(self, src, params, skip=()):
         """Run a batch whose CSR arrays live in host memory (a ReadBatch or a PinnedBatcher) through
         nrq_resquiggle_batch_host.  Results are numpy arrays: views of the batcher's pinned output
-        buffers (valid until its next reset) or fresh arrays for a ReadBatch."""
+        buffers (valid until its next reset) or fresh arrays for a ReadBatch.  `skip`: result arrays that are not
+        to be copied back from the device (NULL in nrq_results), e.g. new_segs and ev_start for a caller that only
+        hands the event table on (start is the running sum of length)."""
         R, A = src.n_reads, src.total_align
         pc = params.to_c() if isinstance(params, ResquiggleParams) else params
         hb = _lib.NrqBatch()
@@ -275,6 +277,9 @@ class ResquiggleEngine(object):
         hr = _lib.NrqResults()
         own = hasattr(src, 'reset')  # a PinnedBatcher brings its own output buffers
         for name, (n, dt) in shapes.items():
+            if name in skip:
+                outs[name] = None
+                continue
             arr = getattr(src, name)[:max(n, 1)] if own else np.empty(max(n, 1), dtype=dt)
             outs[name] = arr[:n]
             setattr(hr, name, arr.ctypes.data)

@@ -72,9 +72,10 @@ def _albacore_after_1_0(version):
     return parts > [1, 0]
 
 
-def get_read_data(fast5_fn, basecall_group, basecall_subgroup):
+def get_read_data(fast5_fn, basecall_group, basecall_subgroup, native=True):
     """resquiggle.py:807-907 -> (read_start_rel_to_raw, starts_rel_to_read, basecalls,
-    channel_info, read_id)."""
+    channel_info, read_id).  The event arithmetic and the stay removal (:848-898, :767-805) run in libnrqio
+    (nrqio_events_to_starts); native=False is the numpy mirror the tests hold it against."""
     try:
         f5 = fast5_io.open_fast5(fast5_fn, 'r')
     except Exception:
@@ -97,6 +98,14 @@ def get_read_data(fast5_fn, basecall_group, basecall_subgroup):
         raise RuntimeError(msg.CHANNEL_INFO)
 
     rate = channel.sampling_rate
+    if native:
+        from . import _libio
+        st, starts, bases, read_start = _libio.events_to_starts(
+            events, _albacore_after_1_0(version), int(rate), int(raw_attrs['start_time']))
+        if st != _libio.FE_OK:
+            text = _libio.fe_message(st)
+            raise (RuntimeError if st == _libio.FE_ALL_STAYS else NotImplementedError)(text)
+        return read_start, starts, np.frombuffer(bases, dtype='S1').astype('U1'), channel, raw_attrs['read_id']
     first_sample = np.round(events['start'][0].astype(np.float64) * rate).astype(np.uint64)
     raw_t0 = raw_attrs['start_time']
     if first_sample >= raw_t0:
@@ -124,7 +133,28 @@ def get_read_data(fast5_fn, basecall_group, basecall_subgroup):
     return read_start, starts, basecalls, channel, raw_attrs['read_id']
 
 
+def get_read_data_py(fast5_fn, basecall_group, basecall_subgroup):
+    """the numpy mirror of resquiggle.py:807-907 (test reference for the native path)"""
+    return get_read_data(fast5_fn, basecall_group, basecall_subgroup, native=False)
+
+
 # ------------------------------------------------------------------ SAM record -> alignment
+def parse_sam_record_native(record, genome_index):
+    """parse_sam_record through libnrqio (nrqio_sam_to_rows); same return value, same exceptions"""
+    from . import _libio
+    st, rr, gr, clip, _ = _libio.sam_to_rows(record['cigar'], int(record['flag']), int(record['pos']),
+                                             record['seq'], genome_index[record['rName']])
+    if st == _libio.FE_BAD_CIGAR:
+        raise RuntimeError(msg.BAD_CIGAR)
+    if st == _libio.FE_SEQ_CIGAR_DISAGREE:
+        raise AssertionError(msg.SEQ_CIGAR_DISAGREE)
+    if st != _libio.FE_OK:
+        raise RuntimeError(_libio.fe_message(st))
+    reverse = bool(int(record['flag']) & 0x10)
+    return ((rr.decode(), gr.decode()), genomeLoc(int(record['pos']) - 1, '-' if reverse else '+', record['rName']),
+            clip[0], clip[1])
+
+
 def parse_sam_record(record, genome_index):
     """resquiggle.py:583-660 -> ((read row, genome row), genomeLoc, start_clipped, end_clipped).
 
@@ -180,16 +210,19 @@ def parse_sam_record(record, genome_index):
     ri = gi = 0
     for n, op in ops:
         if op in _ALIGNED:
-            read_row.append(read[ri:ri + n])
-            ref_row.append(ref[gi:gi + n])
+            # zip(qSeq[:n], tSeq[:n]) (:646): as many pairs as the shorter of the two has (the reference sequence
+            # runs short when a leading / trailing insertion was trimmed from it, :626, :632)
+            pairs = min(len(read[ri:ri + n]), len(ref[gi:gi + n]))
+            read_row.append(read[ri:ri + pairs])
+            ref_row.append(ref[gi:gi + pairs])
             ri += n
             gi += n
         elif op in _READ_ONLY:
             read_row.append(read[ri:ri + n])
-            ref_row.append('-' * n)
+            ref_row.append('-' * len(read[ri:ri + n]))
             ri += n
         else:
-            read_row.append('-' * n)
+            read_row.append('-' * len(ref[gi:gi + n]))
             ref_row.append(ref[gi:gi + n])
             gi += n
     rows = (''.join(read_row), ''.join(ref_row))
@@ -216,7 +249,7 @@ def parse_sam_output(align_output, batch_reads_data, genome_index):
             failed.append((msg.NO_ALIGNMENT, name))
             continue
         try:
-            parsed[name] = parse_sam_record(rec, genome_index)
+            parsed[name] = parse_sam_record_native(rec, genome_index)
         except Exception as e:  # noqa: BLE001 -- per-read failure, like the reference
             failed.append((str(e), name))
     return failed, parsed

@@ -846,11 +846,44 @@ class Writer(object):
 
 
 # =====================================================================================  file object
-def load_tree(data):
-    """HDF5 bytes -> (fast5_io.MemGroup tree with lazily decoded datasets, reasons a rewrite would be lossy)"""
+# A group whose members are decoded from the file when somebody first asks for them: a read-only open of a FAST5
+# file touches four or five of its twenty-odd objects (resquiggle.py:328-341).
+def _lazy_group_class():
+    from . import fast5_io as f5
+
+    class LazyGroup(f5.MemGroup):
+        def __init__(self, build, links):
+            f5.MemGroup.__init__(self)
+            self.__dict__.pop('_children', None)
+            self._build, self._links, self._members = build, links, None
+
+        @property
+        def _children(self):
+            if self._members is None:
+                self._members = {}
+                for name, child in self._links:
+                    self._members[name] = self._build(child)
+            return self._members
+
+        @_children.setter
+        def _children(self, value):  # MemGroup.__init__ assigns an empty dict
+            pass
+
+    return LazyGroup
+
+
+_LAZY_GROUP = []
+
+
+def load_tree(data, lazy=False):
+    """HDF5 bytes -> (fast5_io.MemGroup tree with lazily decoded datasets, reasons a rewrite would be lossy).
+    lazy: groups decode their members on first access as well (read-only opens); `lossy` is then only complete for
+    what has been visited, which is why files opened for writing are always decoded whole."""
     from . import fast5_io as f5
     rd = Reader(data)
     seen = {}
+    if lazy and not _LAZY_GROUP:
+        _LAZY_GROUP.append(_lazy_group_class())
 
     def build(addr):
         if addr in seen:
@@ -859,9 +892,12 @@ def load_tree(data):
         msgs = rd.messages(addr)
         links = rd.links(msgs)
         if links is not None:
-            node = f5.MemGroup()
-            for name, child in links:
-                node._children[name] = build(child)
+            if lazy:
+                node = _LAZY_GROUP[0](build, links)
+            else:
+                node = f5.MemGroup()
+                for name, child in links:
+                    node._children[name] = build(child)
         else:
             ds = rd.dataset(msgs)
             if ds is None:
@@ -896,7 +932,7 @@ class NativeFile(object):
         else:
             with open(name, 'rb') as fp:
                 data = fp.read()
-            self._root, lossy = load_tree(data)
+            self._root, lossy = load_tree(data, lazy=(mode == 'r'))
             self._dirty = False
             if mode != 'r' and lossy:
                 raise Unsupported('refusing to rewrite %s: %s' % (name, '; '.join(sorted(set(lossy)))))

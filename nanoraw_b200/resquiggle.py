@@ -285,7 +285,9 @@ class BatchPipeline(object):
             norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=self.outlier_thresh,
             compute_sd=self.compute_sd, num_cpts_limit=self.num_cpts_limit, timeout=self.timeout,
             min_event_obs=self.min_event_obs)
-        res = engine.run_host(batcher, params)
+        # new_segs / ev_start (both recoverable from ev_length) and the accounting arrays stay on the device
+        res = engine.run_host(batcher, params, skip=('new_segs', 'ev_start', 'region_samples', 'n_indels')
+                              if self.in_place else ())
         # the four datasets of every read as gzip chunks, straight from the pinned result arrays (libnrqio threads):
         # no per-read event tables are built on this side, and the I/O processes neither deflate nor see numpy arrays
         chunks = off = ln = None

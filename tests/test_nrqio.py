@@ -92,6 +92,16 @@ def test_pack_corrected_matches_numpy(threads):
         assert np.array_equal(np.frombuffer(zlib.decompress(parts[3]), '<i8'), rd.starts)
     assert _libio.load().nrqio_pack_corrected(C.byref(hb), C.byref(hr), 0, batch.n_reads, 1, buf.ctypes.data, 10,
                                               off.ctypes.data, ln.ctypes.data) == -1  # output too small
+    # without the start column (not copied back from the device): rebuilt as the running sum of length from starts[0]
+    hr.ev_start = None
+    buf, off, ln = _libio.pack_corrected(hb, hr, batch.n_reads, threads=threads)
+    for r, rd in enumerate(reads):
+        if r == 3:
+            continue
+        o, n = int(batch.align_off[r]), int(outs['n_bases'][r])
+        ev = np.frombuffer(zlib.decompress(buf[off[4 * r]:off[4 * r] + ln[4 * r]].tobytes()), dtype=EVENT_DTYPE)
+        want = int(rd.starts[0]) + np.concatenate([[0], np.cumsum(outs['ev_length'][o:o + n][:-1], dtype=np.uint64)])
+        assert np.array_equal(ev['start'], want.astype(np.uint32)) and np.array_equal(ev['length'], outs['ev_length'][o:o + n])
 
 
 def _tree(node):
