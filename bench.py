@@ -273,21 +273,15 @@ def spot_check(engine, host_batch, reads, out_dev, n_check=2):
 def gpu_arm(args):
     import torch
     import torch.distributed as dist
-    from nanoraw_b200 import _lib
+    from nanoraw_b200 import _lib, distributed
     from nanoraw_b200.batch import ReadBatch
     from nanoraw_b200.engine import ResquiggleEngine, ResquiggleParams, DeviceResults
 
-    rank = int(os.environ.get('RANK', '0'))
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        torch.cuda.set_device(local)
-        # stdout carries the one JSON line and nothing else: NCCL's own messages (its version banner under
-        # NCCL_DEBUG=VERSION/WARN/INFO) go to stderr
-        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    else:
-        torch.cuda.set_device(0)
+    # stdout carries the one JSON line and nothing else: NCCL's own messages (its version banner under
+    # NCCL_DEBUG=VERSION/WARN/INFO) go to stderr
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
+    rank, world, local = distributed.init('nccl')  # one process per GPU; no collective on the data path
+    torch.cuda.set_device(local)
     engine = ResquiggleEngine()
     lib = engine.lib
     dev = engine.device
@@ -312,8 +306,7 @@ def gpu_arm(args):
         rank, db.n_reads, db.device_bytes() / 1e9, out.device_bytes() / 1e9, ws.numel() / 1e9))
 
     def barrier():
-        if world > 1:
-            dist.barrier()
+        distributed.barrier()
         torch.cuda.synchronize()
 
     # ---- warm-up, then the timed kernel-only region
@@ -364,13 +357,8 @@ def gpu_arm(args):
     e2e_samples, e2e_ms, h2d, d2h = e2e_leg(args, lib, _lib, e2e_batch, pc, local, barrier)
 
     # ---- reduce over ranks: max time, summed work
-    vals = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device=dev)
-    sums = torch.tensor([samples_ok, reads_ok, e2e_samples, launches], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    elapsed_ms, e2e_ms = vals.tolist()
-    samples_all, reads_all, e2e_samples_all, launches_all = sums.tolist()
+    (elapsed_ms, e2e_ms), (samples_all, reads_all, e2e_samples_all, launches_all) = distributed.combine(
+        [elapsed_ms, e2e_ms], [samples_ok, reads_ok, e2e_samples, launches], device=dev)
 
     if rank == 0:
         ms_per_step = elapsed_ms / max(args.steps, 1)
@@ -427,16 +415,11 @@ def gpu_arm(args):
         if world > 1:
             os.environ['NRQ_IO_PROCS'] = str(max(2, host_cores() // world))
         f5 = fast5_leg(args, reads, barrier)
-        agg = torch.tensor([f5['ok_samples'], f5['files'] - f5['failed_reads'], f5['failed_reads']],
-                           dtype=torch.float64, device=dev)
-        tmax = torch.tensor([f5['seconds']], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        (dt,), agg = distributed.combine([f5['seconds']], [f5['ok_samples'], f5['files'] - f5['failed_reads'],
+                                                           f5['failed_reads']], device=dev)
         if rank == 0:
-            dt = float(tmax.item())
-            f5.update({'value': float(agg[0].item()) / dt, 'reads_per_s': float(agg[1].item()) / dt,
-                       'files': args.fast5_files * world, 'failed_reads': int(agg[2].item()), 'seconds': dt,
+            f5.update({'value': agg[0] / dt, 'reads_per_s': agg[1] / dt,
+                       'files': args.fast5_files * world, 'failed_reads': int(agg[2]), 'seconds': dt,
                        'n_gpus': world, 'host_cores': host_cores()})
             del f5['ok_samples']
             line['e2e_fast5'] = f5
@@ -445,7 +428,7 @@ def gpu_arm(args):
     if rank == 0:
         emit(line)
     if world > 1:
-        dist.barrier()
+        distributed.barrier()
         dist.destroy_process_group()
 
 
@@ -749,7 +732,7 @@ def main():
     ap.add_argument('--ref-reads', type=int, default=None)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--debug-flags', type=int, default=0, help='nrq_params.debug_flags (4 = no speculative search)')
-    ap.add_argument('--fast5-files', type=int, default=4096,
+    ap.add_argument('--fast5-files', type=int, default=8192,
                     help='FAST5 files on disk per GPU for the e2e_fast5 leg (0 = skip)')
     ap.add_argument('--divergence-reads', type=int, default=1024,
                     help='reads compared with the reference\'s default argsort order (N = 1; 0 = skip)')

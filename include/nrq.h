@@ -184,6 +184,14 @@ int nrq_genome_aggregate(const int32_t* read_start, const int32_t* read_len, con
                          int32_t* coverage, double* mean_of_means, double* mean_of_sds, double* mean_of_lengths,
                          void* stream);
 
+/* f-3, the per-position event lists of get_reads_events (nanoraw_helper.py:446-484) for one track laid out as for
+ * nrq_genome_aggregate: pos_off int64[track_len + 1] = exclusive prefix sum of that call's coverage; the event means
+ * of the reads covering position p are written to values[pos_off[p] .. pos_off[p + 1]) in the order of the track's
+ * reads.  All pointers are device pointers. */
+int nrq_genome_event_lists(const int32_t* read_start, const int32_t* read_len, const int64_t* ev_off,
+                           const uint8_t* read_rev, int32_t n_track_reads, int32_t max_len, int32_t track_len,
+                           const double* norm_mean, const int64_t* pos_off, double* values, void* stream);
+
 /* The whole path a1..a7 for a batch resident in device memory (the body of resquiggle_worker's loop,
  * resquiggle.py:424-433, minus FAST5 I/O).  workspace: device, >= nrq_workspace_bytes(). */
 int nrq_resquiggle_batch(const nrq_batch* b, const nrq_params* p, const nrq_results* out,

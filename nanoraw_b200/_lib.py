@@ -52,6 +52,7 @@ SYMBOLS = {
     'nrq_running_diffs': (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P, _P]),
     'nrq_genome_aggregate': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P,
                                        _P, _P, _P]),
+    'nrq_genome_event_lists': (C.c_int, [_P, _P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P]),
     'nrq_event_table': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams), _P, _P, _P, _P, _P, _P,
                                   _P, _P, _P, _P]),
     'nrq_resquiggle_batch': (C.c_int, [C.POINTER(NrqBatch), C.POINTER(NrqParams),

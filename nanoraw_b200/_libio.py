@@ -83,7 +83,7 @@ def pack_threads():
         cores = len(os.sched_getaffinity(0))
     except Exception:
         cores = os.cpu_count() or 1
-    return max(1, min(8, cores // 2))
+    return max(1, min(16, cores))
 
 
 def pack_corrected(c_batch, c_results, n_reads, threads=None):

@@ -49,4 +49,33 @@ k_genome_aggregate(const int32_t* __restrict__ start, const int32_t* __restrict_
   mean_of_lengths[p] = cov ? __ddiv_rn(sl, (double)cov) : qnan;
 }
 
+// get_reads_events (nanoraw_helper.py:446-484): the event means of every read that covers a position, per
+// position.  pos_off = exclusive prefix of the coverage (one entry more than the track); the means of position p go
+// to values[pos_off[p] ..), in the order of the track's reads (sorted by mapped start; the reference's order inside
+// one position is that of an unstable argsort, i.e. unspecified).
+__global__ void __launch_bounds__(256)
+k_genome_event_lists(const int32_t* __restrict__ start, const int32_t* __restrict__ n,
+                     const int64_t* __restrict__ ev_off, const uint8_t* __restrict__ rev, int n_track_reads,
+                     int max_len, int track_len, const double* __restrict__ norm_mean,
+                     const int64_t* __restrict__ pos_off, double* __restrict__ values) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= track_len) return;
+  int lo = 0, hi = n_track_reads;
+  const int first_start = p - max_len + 1;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (start[mid] < first_start) lo = mid + 1; else hi = mid; }
+  const int k0 = lo;
+  hi = n_track_reads;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (start[mid] <= p) lo = mid + 1; else hi = mid; }
+  const int k1 = lo;
+  double* o = values + pos_off[p];
+  const int64_t cap = pos_off[p + 1] - pos_off[p];
+  int64_t w = 0;
+  for (int k = k0; k < k1 && w < cap; ++k) {
+    const int d = p - start[k];
+    const int len = n[k];
+    if (d >= len) continue;
+    o[w++] = norm_mean[ev_off[k] + (rev[k] ? len - 1 - d : d)];
+  }
+}
+
 }  // namespace nrq

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost nothing unless a profiler is attached
+
 #include "nrq_indels.cu"
 #include "nrq_norm.cu"
 #include "nrq_speculate.cu"
@@ -37,6 +39,13 @@ int fail(const char* what, cudaError_t e = cudaSuccess) {
   } while (0)
 
 inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// NVTX range over a scope: the four stages of a batch and the copy pipeline of the host entry point show up as
+// named ranges on the timeline (tracing)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 // device-filling grids of the two persistent kernels, worked out once per device (a process may drive several)
 struct DeviceGrids {
@@ -306,6 +315,19 @@ int nrq_genome_aggregate(const int32_t* read_start, const int32_t* read_len, con
   return 0;
 }
 
+int nrq_genome_event_lists(const int32_t* read_start, const int32_t* read_len, const int64_t* ev_off,
+                           const uint8_t* read_rev, int32_t n_track_reads, int32_t max_len, int32_t track_len,
+                           const double* norm_mean, const int64_t* pos_off, double* values, void* stream) {
+  if (!pos_off || !values) return fail("nrq_genome_event_lists: NULL output");
+  if (n_track_reads > 0 && (!read_start || !read_len || !ev_off || !read_rev || !norm_mean))
+    return fail("nrq_genome_event_lists: NULL input");
+  if (track_len <= 0 || n_track_reads <= 0) return 0;
+  nrq::k_genome_event_lists<<<(track_len + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      read_start, read_len, ev_off, read_rev, n_track_reads, max_len, track_len, norm_mean, pos_off, values);
+  NRQ_CHECK_LAUNCH("k_genome_event_lists");
+  return 0;
+}
+
 int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale_values,
                     const int32_t* n_bases, const int32_t* new_segs, const int32_t* status,
                     double* norm_mean, double* norm_stdev, uint32_t* ev_start, uint32_t* ev_length,
@@ -346,18 +368,27 @@ static int resquiggle_batch_impl(const nrq_batch* b, const nrq_params* p, const 
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], s); };
 
+  NvtxRange batch_range("nrq batch (a1..a7)");
   mark(0);
+  nvtxRangePushA("a2 indel scan");
   if (int e = nrq_find_indels(b, out->status, out->n_indels, out->n_bases, w.indel_off, w.indels, w.indel_cap,
                               out->ev_base, stream))
-    return e;
+    { nvtxRangePop(); return e; }
+  nvtxRangePop();
   mark(1);
-  if (int e = nrq_norm_stats(b, p, out->status, out->scale_values, stream)) return e;
+  {
+    NvtxRange r("a1 order statistics");
+    if (int e = nrq_norm_stats(b, p, out->status, out->scale_values, stream)) return e;
+  }
   mark(2);
+  nvtxRangePushA("a3-a6 re-segmentation");
   if (int e = resegment_impl(b, p, out->scale_values, w.indel_off, w.indels, out->n_bases, w.groups, w.spec, w.indel_cap, w.big,
                              w.big_doubles, w.work_counter, out->status, out->new_segs, out->region_samples, nullptr,
                              stream, ev ? ev[5] : nullptr))
-    return e;
+    { nvtxRangePop(); return e; }
+  nvtxRangePop();
   mark(3);
+  NvtxRange ev_range("a7 event table");
   if (int e = nrq_event_table(b, p, out->scale_values, out->n_bases, out->new_segs, out->status, out->norm_mean,
                               out->norm_stdev, out->ev_start, out->ev_length, out->ev_base, stream))
     return e;
@@ -527,6 +558,7 @@ int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, cons
     };
     while (hi < R && (hi == lo || in_bytes(lo, hi + 1) <= kChunkBytes)) ++hi;
     const int n = hi - lo;
+    NvtxRange chunk_range("host chunk: H2D, kernels, D2H queued");
     nrq_slot& sl = h->slots[chunk_index % h->n_slots];
     cudaStream_t s = sl.stream;
     // the slot's buffers and pinned offset staging are reused below: wait for its previous chunk's download

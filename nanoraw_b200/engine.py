@@ -447,6 +447,43 @@ class ResquiggleEngine(object):
             _lib.check(rc, 'nrq_genome_aggregate')
         return (cov.cpu().numpy()[:L], o_m.cpu().numpy()[:L], o_s.cpu().numpy()[:L], o_l.cpu().numpy()[:L])
 
+    def genome_event_lists(self, starts, lengths, reverse, means, track_len):
+        """get_reads_events (nanoraw_helper.py:446-484) for one (chromosome, strand) track: the event means of every
+        read covering a position.  -> (coverage int64[L], pos_off int64[L + 1], values float64[pos_off[-1]])."""
+        t = self.torch
+        L = int(track_len)
+        order = np.argsort(np.asarray(starts), kind='stable')
+        n_reads = len(order)
+        if n_reads == 0 or L <= 0:
+            return np.zeros(max(L, 0), np.int64), np.zeros(max(L, 0) + 1, np.int64), np.zeros(0)
+        st = np.asarray(starts, dtype=np.int32)[order]
+        ln = np.asarray(lengths, dtype=np.int32)[order]
+        rv = np.asarray(reverse, dtype=np.uint8)[order]
+        off = np.zeros(n_reads + 1, dtype=np.int64)
+        np.cumsum(ln, out=off[1:])
+        cat = np.concatenate([np.asarray(means[i], dtype=np.float64) for i in order])
+        zeros = np.zeros(len(cat))
+        with t.cuda.device(self.device):
+            dev = lambda a: t.from_numpy(np.ascontiguousarray(a)).to(self.device)
+            d_st, d_ln, d_rv, d_off, d_m = dev(st), dev(ln), dev(rv), dev(off[:-1]), dev(cat)
+            d_z = dev(zeros)
+            d_zl = t.zeros(len(cat), dtype=t.int32, device=self.device)
+            cov = t.empty(L, dtype=t.int32, device=self.device)
+            scratch = [t.empty(L, dtype=t.float64, device=self.device) for _ in range(3)]
+            rc = self.lib.nrq_genome_aggregate(
+                _ptr(d_st), _ptr(d_ln), _ptr(d_off), _ptr(d_rv), n_reads, int(ln.max()), L, _ptr(d_m), _ptr(d_z),
+                _ptr(d_zl), _ptr(cov), _ptr(scratch[0]), _ptr(scratch[1]), _ptr(scratch[2]), self._stream())
+            _lib.check(rc, 'nrq_genome_aggregate')
+            pos_off = t.zeros(L + 1, dtype=t.int64, device=self.device)
+            pos_off[1:] = t.cumsum(cov.to(t.int64), 0)  # offsets only: plumbing, the lists are filled by the kernel
+            total = int(pos_off[-1].item())
+            values = t.empty(max(total, 1), dtype=t.float64, device=self.device)
+            rc = self.lib.nrq_genome_event_lists(
+                _ptr(d_st), _ptr(d_ln), _ptr(d_off), _ptr(d_rv), n_reads, int(ln.max()), L, _ptr(d_m),
+                _ptr(pos_off), _ptr(values), self._stream())
+            _lib.check(rc, 'nrq_genome_event_lists')
+        return cov.cpu().numpy().astype(np.int64), pos_off.cpu().numpy(), values.cpu().numpy()[:total]
+
     def running_diffs(self, norm_signal, min_seg_len=4):
         """plot_commands.py:225-229: the running-difference trace of a normalised signal window."""
         t = self.torch

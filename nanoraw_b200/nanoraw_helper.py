@@ -244,6 +244,27 @@ def get_base_stats(raw_read_coverage, chrm_sizes):
     return out
 
 
+def get_reads_events(chrm_strand_reads, rev_strand):
+    """nanoraw_helper.py:446-484: {genomic position: event means of the reads that cover it} for reads of ONE
+    chromosome and strand; None when no read has an event table.  The lists are put together on the GPU
+    (nrq_genome_event_lists).  The reference orders the means of one position by an unstable argsort of the
+    positions, i.e. in no specified order; here they come in the order of the reads' mapped starts."""
+    from .engine import get_engine
+    starts, means = [], []
+    for r_data in chrm_strand_reads:
+        c = _read_event_columns(r_data)
+        if c is None:
+            continue
+        starts.append(r_data.start)
+        means.append(c[0])
+    if not starts:
+        return None
+    track_len = max(s + len(m) for s, m in zip(starts, means))
+    cov, off, values = get_engine().genome_event_lists(
+        starts, [len(m) for m in means], [bool(rev_strand)] * len(means), means, track_len)
+    return dict((int(p), values[off[p]:off[p + 1]]) for p in np.flatnonzero(cov > 0))
+
+
 def get_coverage(raw_read_coverage):
     """nanoraw_helper.py:298-308: coverage over [start, end) of every read, up to the largest end."""
     from .engine import get_engine

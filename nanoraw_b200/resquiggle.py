@@ -34,7 +34,7 @@ from .frontend import (  # noqa: F401  (re-exported call surface)
 VERBOSE = False
 
 # reads per device batch in the re-squiggle worker (additive knob, not a reference option)
-DEVICE_BATCH_READS = int(os.environ.get('NANORAW_B200_BATCH_READS', '4096'))
+DEVICE_BATCH_READS = int(os.environ.get('NANORAW_B200_BATCH_READS', '2048'))
 
 indelStats = namedtuple('indelStats', ('start', 'end', 'diff'))  # :29-30
 indelGroupStats = namedtuple('indelGroupStats', ('start', 'end', 'cpts', 'indels'))  # :31-32

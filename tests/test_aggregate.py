@@ -87,3 +87,20 @@ def test_device_aggregation_matches_reference():
             # the reference adds in file order, the kernel in mapped-start order: float64 rounding only
             assert np.all(np.abs(got[key][ok] - want[ok]) <= 1e-12 * np.maximum(1.0, np.abs(want[ok])))
     assert np.array_equal(nh.get_base_means(rrc, sizes)[('chrA', '+')], means[('chrA', '+')], equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_device_reads_events_match_reference():
+    """get_reads_events (nanoraw_helper.py:446-484) against tests/golden/reads_events_v1.npz, made by the real
+    reference over the same corrected reads: same positions, same event means per position (as multisets: the
+    reference's order inside a position comes from an unstable argsort)"""
+    from nanoraw_b200 import nanoraw_helper as nh
+    G = np.load(os.path.join(HERE, 'golden', 'reads_events_v1.npz'))
+    rrc = nh.parse_fast5s(_write_corrected_files(), 'RawGenomeCorrected_000', ['BaseCalled_template'])
+    for k, key in enumerate(TRACKS):
+        got = nh.get_reads_events(rrc[key], key[1] == '-')
+        pos, off, vals = G['t%d/pos' % k], G['t%d/off' % k], G['t%d/values' % k]
+        assert sorted(got) == pos.tolist()
+        for i, p in enumerate(pos.tolist()):
+            assert np.array_equal(np.sort(got[p]), vals[off[i]:off[i + 1]]), (key, p)
+    assert nh.get_reads_events([], False) is None

@@ -2,6 +2,8 @@
 oracle.  Bit-exact: boundaries, scale values, normalised signal; event means / sds are also
 compared exactly (the kernel follows numpy's summation order), with the contract's 1e-9
 tolerance as the documented fallback bar."""
+import os
+
 import numpy as np
 import pytest
 
@@ -181,10 +183,31 @@ def test_golden_normalised_signal(engine):
 SEEDED = {
     'standard_10kb': (synth.SynthConfig(seed_base=41000), 6),
     'short_4kb': (synth.config_short(42000), 8),
-    'indel_dense': (synth.config_indel_dense(43000), 4),
+    'indel_dense': (synth.config_indel_dense(43000), 32),        # BASELINE configs[4]: 12 % / 12 % indels, 50-500 clips
     'low_dwell': (synth.SynthConfig(span_mean=3000, span_sd=300, dwell_mean=6.2, seed_base=44000), 6),
-    'long_100kb': (synth.SynthConfig(span_mean=100_000, span_sd=5_000, seed_base=45000), 1),
+    'long_100kb': (synth.SynthConfig(span_mean=100_000, span_sd=5_000, seed_base=45000), 32),  # configs[3]
 }
+
+
+def _oracle_job(read):
+    return orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts, read.read_align.decode(),
+                               read.genome_align.decode())
+
+
+_ORACLE_CACHE = {}
+
+
+def seeded_reads_and_oracle(name):
+    """the seeded reads of one configuration and what the oracle makes of them (once per session; the oracle runs
+    on all host cores: a 100 kb read takes it more than a second)"""
+    if name not in _ORACLE_CACHE:
+        import multiprocessing as mp
+        cfg, n = SEEDED[name]
+        reads = synth.make_reads(n, cfg, genome=synth.make_genome(1_000_000, seed=9))
+        with mp.get_context('fork').Pool(min(len(reads), len(os.sched_getaffinity(0)))) as pool:
+            outs = pool.map(_oracle_job, reads, chunksize=1)
+        _ORACLE_CACHE[name] = (reads, outs)
+    return _ORACLE_CACHE[name]
 
 
 def assert_same_results(a, b, n_reads):
@@ -208,7 +231,7 @@ def test_speculative_search_changes_nothing(engine, name):
         reads = synth.make_reads(3, synth.SynthConfig(span_mean=150, span_sd=30, seed_base=71000), genome=genome)
     else:
         cfg, _ = SEEDED[name]
-        reads = synth.make_reads(12, cfg, genome=genome)
+        reads = synth.make_reads(12, cfg, genome=genome)[:12]
     batch = ReadBatch.from_reads(reads)
     on = engine.run(batch, ResquiggleParams())
     off = engine.run(batch, ResquiggleParams(debug_flags=4))
@@ -253,13 +276,10 @@ def test_speculative_search_at_the_edges_of_the_raw_array(engine):
 @pytest.mark.parametrize('name', list(SEEDED))
 def test_seeded_reads_against_oracle(engine, name, exact_stats):
     from nanoraw_b200.engine import ResquiggleParams
-    cfg, n = SEEDED[name]
-    genome = synth.make_genome(1_000_000, seed=9)
-    reads = synth.make_reads(n, cfg, genome=genome)
+    reads, outs = seeded_reads_and_oracle(name)
     res = engine.run(ReadBatch.from_reads(reads), ResquiggleParams(exact_stats=exact_stats))
     for r, read in enumerate(reads):
-        out = orc.resquiggle_read(read.raw, read.read_start_rel_to_raw, read.starts,
-                                  read.read_align.decode(), read.genome_align.decode())
+        out = outs[r]
         assert res.ok(r), res.error(r)
         assert res.scale_values_of(r) == tuple(float(v) for v in out['scale_values'])
         assert np.array_equal(res.new_segs_of(r), out['new_segs'])
@@ -524,7 +544,12 @@ def test_malformed_reads_get_a_status_and_do_not_disturb_their_neighbours(engine
     assert res.status[1] == _lib.ST_BAD_ALIGNMENT
     assert res.status[2] == _lib.ST_BAD_INPUT
     assert res.status[3] in (_lib.ST_BAD_INPUT, _lib.ST_PAST_END)
-    assert res.status[4] in (_lib.ST_ZERO_LEN, _lib.ST_OK)
+    try:  # whatever the oracle makes of it (zero-length unless an indel group happens to replace that boundary)
+        orc.resquiggle_read(bad[4].raw, bad[4].read_start_rel_to_raw, bad[4].starts, bad[4].read_align.decode(),
+                            bad[4].genome_align.decode())
+        assert res.status[4] == _lib.ST_OK
+    except Exception as e:  # noqa: BLE001
+        assert res.error(4) == str(e)
     for r in (0, 5):
         assert res.ok(r)
         assert np.array_equal(res.new_segs_of(r), want.new_segs_of(r))

@@ -54,11 +54,37 @@ def test_oracle_matches_reference_stable(case):
         assert np.array_equal(a['read_segments'], case.read.starts)
 
 
+def _reachable_by_tie_breaks(rd, K, target, m=4):
+    """can the greedy selection (resquiggle.py:244-254) end on exactly `target` if, whenever several candidates
+    share the largest running difference EXACTLY, it may take any of them?  (That is all an unstable argsort can
+    change: positions are visited in descending value, equal values in arbitrary order.)"""
+    n = len(rd)
+    target = frozenset(target)
+
+    def go(black, picked):
+        if len(picked) == K:
+            return frozenset(picked) == target
+        free = [i for i in range(n) if i not in black]
+        if not free:
+            return False
+        top = max(rd[i] for i in free)
+        ties = [i for i in free if rd[i] == top]
+        for i in ties:
+            if i not in target:
+                continue  # a pick outside the target can never be undone
+            if go(black | set(range(i - m + 1, i + m + 1)), picked + [i]):
+                return True
+        return False
+
+    return go(frozenset(), [])
+
+
 def test_default_sort_tie_attribution():
-    """Where the reference's own (unstable) argsort order picked different
-    change-points on the generating host, the difference must be explained by
-    exact ties in the running differences."""
-    n_diff = 0
+    """Where the reference's own (unstable) argsort order picked different change-points on the generating host,
+    the difference must be explained by EXACT ties in the running differences: the default
+    result has to be reachable from the same running differences by breaking ties between exactly equal maxima
+    differently, and the first pick at which the two selections part must be such a tie."""
+    n_diff = n_groups = 0
     for case in CASES:
         if case.error or not case.meta['default_differs']:
             continue
@@ -74,7 +100,21 @@ def test_default_sort_tie_attribution():
             pos += len(mine)
             if mine == theirs:
                 continue
-            rd = orc.running_diffs(sig[starts[g.start]:starts[g.end]])
-            # a differing pick means some value is duplicated in this region
-            assert len(np.unique(rd)) < len(rd), (case.name, g.start, g.end)
-    assert n_diff > 0
+            n_groups += 1
+            t0 = int(starts[g.start])
+            rd = orc.running_diffs(sig[t0:starts[g.end]])
+            K = len(mine)
+            want = [c - t0 - 4 for c in theirs]  # change-point -> running-difference index
+            assert _reachable_by_tie_breaks(rd, K, want), (case.name, g.start, g.end)
+            # the stable selection, pick by pick: the first pick that is not in the default set ties exactly with a
+            # candidate that is
+            black, default_set = set(), set(want)
+            order = sorted(range(len(rd)), key=lambda i: (rd[i], i), reverse=True)
+            for _ in range(K):
+                p = next(i for i in order if i not in black)
+                if p not in default_set:
+                    rivals = [i for i in default_set if i not in black and rd[i] == rd[p]]
+                    assert rivals, (case.name, g.start, g.end, p)
+                    break
+                black.update(range(p - 3, p + 5))
+    assert n_diff > 0 and n_groups > 0
