@@ -285,7 +285,8 @@ def gpu_arm(args):
     engine = ResquiggleEngine()
     lib = engine.lib
     dev = engine.device
-    params = ResquiggleParams(debug_flags=args.debug_flags)
+    # the device entry point cannot see read lengths: say that the long-read workload holds reads to stream in parts
+    params = ResquiggleParams(debug_flags=args.debug_flags, long_read_parts=16 if args.config == 'long' else 0)
     pc = params.to_c()
 
     # ---- synthetic reads: `unique` per rank on the host, tiled to `reads` on the device
@@ -414,6 +415,9 @@ def gpu_arm(args):
     if args.fast5_files > 0:
         if world > 1:
             os.environ['NRQ_IO_PROCS'] = str(max(2, host_cores() // world))
+            # the host cores are shared by all ranks: fewer files per rank keep the leg's duration about the same
+            from nanoraw_b200 import resquiggle as _rsq
+            args.fast5_files = max(2 * _rsq.DEVICE_BATCH_READS, args.fast5_files // world)
         f5 = fast5_leg(args, reads, barrier)
         (dt,), agg = distributed.combine([f5['seconds']], [f5['ok_samples'], f5['files'] - f5['failed_reads'],
                                                            f5['failed_reads']], device=dev)

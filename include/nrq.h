@@ -66,6 +66,9 @@ typedef struct nrq_params {
   int32_t min_seg_len;      /* min_event_obs, 4 in the reference (resquiggle.py:323) */
   int64_t timeout_ns;       /* --timeout on the device clock; <= 0: none */
   int32_t big_region_cap;   /* samples per warp of global scratch for regions that do not fit shared memory */
+  int32_t long_read_parts;  /* parts (<= 64) in which nrq_event_table streams a read of more than 262 144 samples, one
+                               warp each (BASELINE configs[3]); <= 1: whole reads only.  0 lets the host entry points,
+                               which see the read lengths, decide per chunk; the device entry points treat 0 as 1. */
   int32_t debug_flags;      /* bit0: force the general (bisection) order-statistic path in nrq_norm_stats;
                                bit1: event statistics in numpy's float64 summation order (bit-identical to
                                numpy, slower) instead of exact integer prefix sums (within a few ulps);

@@ -18,7 +18,7 @@ class NrqParams(C.Structure):
         ('norm_type', C.c_int32), ('use_outlier', C.c_int32), ('outlier_thresh', C.c_double),
         ('given_limits', C.c_int32), ('compute_sd', C.c_int32), ('num_cpts_limit', C.c_int32),
         ('min_seg_len', C.c_int32), ('timeout_ns', C.c_int64), ('big_region_cap', C.c_int32),
-        ('debug_flags', C.c_int32)]
+        ('long_read_parts', C.c_int32), ('debug_flags', C.c_int32)]
 
 
 class NrqBatch(C.Structure):

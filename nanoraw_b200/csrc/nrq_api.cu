@@ -1,5 +1,6 @@
 // C ABI of libnrq.so (include/nrq.h).  Unity build: the kernels live in the .cu files included
 // below; this file only validates arguments, carves the workspace and launches.
+#include <algorithm>
 #include <atomic>
 #include <mutex>
 #include <cstdio>
@@ -341,9 +342,16 @@ int nrq_event_table(const nrq_batch* b, const nrq_params* p, const double* scale
   if ((p->debug_flags & 2) || b->norm_signal)
     nrq::k_event_table_exact<<<b->n_reads, nrq::kEvThreads, 0, static_cast<cudaStream_t>(stream)>>>(
         *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
+  else if (p->long_read_parts > 1)
+    // gridDim.y: parts a long read (> 262 144 samples) is streamed in, one warp each; the warps of the other parts
+    // of a shorter read leave at once
+    nrq::k_event_table<true><<<dim3((b->n_reads + nrq::kEvWarps - 1) / nrq::kEvWarps,
+                                    p->long_read_parts > 64 ? 64 : p->long_read_parts),
+                               nrq::kEvWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   else
-    nrq::k_event_table<<<(b->n_reads + nrq::kEvWarps - 1) / nrq::kEvWarps, nrq::kEvWarps * 32, 0,
-                         static_cast<cudaStream_t>(stream)>>>(
+    nrq::k_event_table<false><<<(b->n_reads + nrq::kEvWarps - 1) / nrq::kEvWarps, nrq::kEvWarps * 32, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
         *b, *p, scale_values, n_bases, new_segs, status, norm_mean, norm_stdev, ev_start, ev_length);
   NRQ_CHECK_LAUNCH("k_event_table");
   return 0;
@@ -626,7 +634,13 @@ int64_t nrq_resquiggle_batch_host_submit(nrq_handle* h, const nrq_batch* b, cons
     if (err != cudaSuccess) break;
     cudaEventRecord(sl.up_done, h->h2d);
     cudaStreamWaitEvent(s, sl.up_done, 0);
-    rc = nrq_resquiggle_batch(&d, p, &o, ws, ws_bytes, s);
+    nrq_params pp = *p;
+    if (pp.long_read_parts == 0) {  // the read lengths are in host memory here: parts only where a long read is
+      int64_t longest = 0;
+      for (int i = 0; i < n; ++i) longest = std::max<int64_t>(longest, raw_off[i + 1] - raw_off[i]);
+      pp.long_read_parts = longest > 262144 ? 16 : 1;
+    }
+    rc = nrq_resquiggle_batch(&d, &pp, &o, ws, ws_bytes, s);
     if (rc) break;
     cudaEventRecord(sl.k_done, s);
     cudaStreamWaitEvent(h->d2h, sl.k_done, 0);

@@ -315,9 +315,12 @@ __device__ __forceinline__ int2 ev_loc_at(const EvLoc* locw, int sl) {  // pair 
 #define NRQ_EV_AHEAD 2
 #endif
 constexpr int kEvAhead = NRQ_EV_AHEAD;  // steps between a prefetch and the load it serves
+constexpr int kEvLongRead = 262144;     // samples from which a read is streamed in parts (when the launch has any)
+constexpr int kEvPartSamples = 65536;   // ... of about this many samples each
 constexpr int kNoPos = 0x3fffffff;
   // "no such boundary": never inside a step
 
+template <bool PARTS>  // PARTS: long reads are streamed in gridDim.y parts (nrq_params.long_read_parts)
 __global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
               const int32_t* __restrict__ new_segs, const int32_t* __restrict__ status,
@@ -336,17 +339,48 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   const int lane = (int)lane_id();
   ReadGeom g = read_geom(b, r);
   const NormCoef coef = load_coef(sv, r);
-  const int nb = n_bases[r];
+  int nb = n_bases[r];
   const int32_t* segs = new_segs + b.align_off[r] + r;
-  const size_t off = (size_t)b.align_off[r];
-  const int n_norm = g.n_norm;
+  size_t off = (size_t)b.align_off[r];
+  int n_norm = g.n_norm;
+  const EvClass k = ev_classify(coef, (int)g.sig[n_norm / 2]);  // every lane: a handful of divisions
+  // ---- long reads (BASELINE configs[3]: ~1 M samples): one warp would stream the read for milliseconds while
+  // the device idles, so the launch carries gridDim.y parts and a read of more than kEvLongRead samples is cut at
+  // base boundaries into that many (at most) runs of bases, one per warp.  A part is a read of its own from then
+  // on: its samples start at seg0 (the part's first boundary), positions below are relative to that.  The
+  // classification above (pivot, clip codes) is the whole read's, so every part does the same arithmetic.
+  int seg0 = 0;  // (stays a compile-time 0 without PARTS)
+  if (PARTS) {
+    const int parts = n_norm > kEvLongRead ? min((int)gridDim.y, (n_norm + kEvPartSamples - 1) / kEvPartSamples) : 1;
+    const int part = (int)blockIdx.y;
+    if (part >= parts) return;
+    if (parts > 1) {
+      auto first_base_from = [&](long long s) {  // first boundary index in [0, nb] whose position is >= s
+        int lo = 0, hi = nb;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((long long)__ldg(segs + mid) < s) lo = mid + 1; else hi = mid;
+        }
+        return lo;
+      };
+      const int b0 = part == 0 ? 0 : first_base_from((long long)n_norm * part / parts);
+      const int b1 = part + 1 == parts ? nb : first_base_from((long long)n_norm * (part + 1) / parts);
+      if (b0 >= b1) return;
+      seg0 = b0 == 0 ? 0 : __ldg(segs + b0);
+      const int seg1 = b1 == nb ? n_norm : __ldg(segs + b1);
+      g.sig += seg0;
+      n_norm = seg1 - seg0;
+      nb = b1 - b0;
+      segs += b0;
+      off += (size_t)b0;
+    }
+  }
   EvLoc* const locw = loc[warp];
   double* const o_mean = norm_mean + off;
   double* const o_sd = norm_stdev + off;
   uint32_t* const o_start = ev_start + off;
   uint32_t* const o_length = ev_length + off;
 
-  const EvClass k = ev_classify(coef, (int)g.sig[n_norm / 2]);  // every lane: a handful of divisions
   const int u_lo = k.u_lo, u_hi = k.u_hi, pivot = k.pivot;
   EvRead R;
   R.c_off = __dsub_rn((double)pivot, coef.shift);
@@ -377,7 +411,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   auto load_pos = [&](int c) {  // c > 0 (cur only grows, and boundary 0 is the first one resolved)
     const unsigned bidx = (unsigned)(c + lane);
     int q = bidx == (unsigned)nb ? n_norm : kNoPos;
-    if (bidx < (unsigned)nb) q = __ldg(segs + bidx);
+    if (bidx < (unsigned)nb) q = __ldg(segs + bidx) - seg0;
     return q;
   };
   int pos = load_pos(0);
@@ -519,7 +553,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const unsigned o = (unsigned)(cur + lane - 1);
             o_mean[o] = mean;
             o_sd[o] = sd;
-            o_start[o] = (uint32_t)bpos;
+            o_start[o] = (uint32_t)(bpos + seg0);
             o_length[o] = (uint32_t)n;
           }
           const unsigned last = __shfl_sync(0xffffffffu, EC, cntb - 1);
@@ -553,7 +587,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
             o_mean[o] = mean;
             o_sd[o] = sd;
-            o_start[o] = (uint32_t)bpos;
+            o_start[o] = (uint32_t)(bpos + seg0);
             o_length[o] = (uint32_t)n;
           }
           prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
@@ -576,8 +610,8 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         }
         if (inb && bidx >= 1) {
           const int kbase = bidx - 1;
-          const int s_hi = segs[bidx];
-          const int s_lo = (lane == 0) ? segs[kbase] : (kbase == 0 ? segs[0] : bpos);
+          const int s_hi = segs[bidx] - seg0;
+          const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos);
           const int pos0 = (kbase == 0) ? 0 : s_lo;
           const int n = pos - pos0;
           double mean = qnan, sd = qnan;
@@ -597,7 +631,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           }
           norm_mean[off + kbase] = mean;
           norm_stdev[off + kbase] = sd;
-          ev_start[off + kbase] = (uint32_t)s_lo;
+          ev_start[off + kbase] = (uint32_t)(s_lo + seg0);
           ev_length[off + kbase] = (uint32_t)(s_hi - s_lo);
         }
         prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
@@ -694,15 +728,15 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       if (lane == 0) { b1 = prev1; b2 = prev2; bl = prevl; bh = prevh; }
       if (inb && bidx >= 1) {
         const int kbase = bidx - 1;
-        const int s_hi = segs[bidx];
-        const int s_lo = (lane == 0) ? segs[kbase] : (kbase == 0 ? segs[0] : bpos);
+        const int s_hi = segs[bidx] - seg0;
+        const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos);
         const int pos0 = (kbase == 0) ? 0 : s_lo;
         const int n = pos - pos0;
         double mean = qnan, sd = qnan;
         if (n > 0) ev_base_stats(R, n, e1 - b1, e2 - b2, el - bl, eh - bh, mean, sd);
         norm_mean[off + kbase] = mean;
         norm_stdev[off + kbase] = sd;
-        ev_start[off + kbase] = (uint32_t)s_lo;
+        ev_start[off + kbase] = (uint32_t)(s_lo + seg0);
         ev_length[off + kbase] = (uint32_t)(s_hi - s_lo);
       }
       // carry: prefix at the last boundary resolved in this round

@@ -102,6 +102,13 @@ struct BitWriter {
     n = 0;
     return p;
   }
+  // write out the whole bytes that are pending; fewer than 8 bits stay in *b / *cnt; returns the write position
+  uint8_t* finish_to_byte_state(uint64_t* b, int* cnt) {
+    while (n >= 8) { *p++ = (uint8_t)bits; bits >>= 8; n -= 8; }
+    *b = bits;
+    *cnt = n;
+    return p;
+  }
 };
 
 int64_t stored_size(int64_t n) { return 2 + n + 5 * ((n + kStoredMax - 1) / kStoredMax + (n == 0)) + 4; }
@@ -167,12 +174,46 @@ int64_t write_huffman(const uint8_t* src, int64_t n, uint8_t* dst) {
   for (int k = 0; k < 19; ++k) bw.put(k < 3 ? 0 : 4, 3);
   for (int s = 0; s < kSyms; ++s) bw.put(reverse_bits(len[s], 4), 4);
   bw.put(reverse_bits(0, 4), 4);  // the one distance code: length 0
-  for (i = 0; i + 1 < n; i += 2) {
-    const uint32_t e0 = enc[src[i]], e1 = enc[src[i + 1]];
-    bw.put(e0 & 0xffffu, (int)(e0 >> 16));
-    bw.put(e1 & 0xffffu, (int)(e1 >> 16));
+  // literals, four at a time when no code is longer than 14 bits (four codes on top of fewer than 8 pending bits
+  // then fit 64 bits), else three at a time; whole bytes leave with one unaligned 8-byte store (the bound leaves
+  // room for the bytes past the end)
+  {
+    int max_len = 0;
+    for (int s = 0; s < kSyms; ++s) max_len = std::max<int>(max_len, len[s]);
+    uint8_t* q = bw.finish_to_byte_state(&bw.bits, &bw.n);
+    uint64_t acc = bw.bits;
+    int nb = bw.n;  // < 8
+    auto flush = [&]() {
+      std::memcpy(q, &acc, 8);
+      const int bytes = nb >> 3;
+      q += bytes;
+      acc >>= 8 * bytes;  // bytes <= 7
+      nb &= 7;
+    };
+    i = 0;
+    if (max_len <= 14) {
+      for (; i + 3 < n; i += 4) {
+        const uint32_t e0 = enc[src[i]], e1 = enc[src[i + 1]], e2 = enc[src[i + 2]], e3 = enc[src[i + 3]];
+        acc |= (uint64_t)(e0 & 0xffffu) << nb; nb += (int)(e0 >> 16);
+        acc |= (uint64_t)(e1 & 0xffffu) << nb; nb += (int)(e1 >> 16);
+        acc |= (uint64_t)(e2 & 0xffffu) << nb; nb += (int)(e2 >> 16);
+        acc |= (uint64_t)(e3 & 0xffffu) << nb; nb += (int)(e3 >> 16);
+        flush();
+      }
+    } else {
+      for (; i + 2 < n; i += 3) {
+        const uint32_t e0 = enc[src[i]], e1 = enc[src[i + 1]], e2 = enc[src[i + 2]];
+        acc |= (uint64_t)(e0 & 0xffffu) << nb; nb += (int)(e0 >> 16);
+        acc |= (uint64_t)(e1 & 0xffffu) << nb; nb += (int)(e1 >> 16);
+        acc |= (uint64_t)(e2 & 0xffffu) << nb; nb += (int)(e2 >> 16);
+        flush();
+      }
+    }
+    bw.p = q;
+    bw.bits = acc;
+    bw.n = nb;
   }
-  if (i < n) { const uint32_t e0 = enc[src[i]]; bw.put(e0 & 0xffffu, (int)(e0 >> 16)); }
+  for (; i < n; ++i) { const uint32_t e0 = enc[src[i]]; bw.put(e0 & 0xffffu, (int)(e0 >> 16)); }
   bw.put(enc[256] & 0xffffu, (int)(enc[256] >> 16));
   p = bw.finish();
   const uint32_t ad = adler32(src, n);
@@ -203,7 +244,7 @@ constexpr int kRow = 25;  // norm_mean f64, norm_stdev f64, start u32, length u3
 
 extern "C" {
 
-int64_t nrqio_deflate_bound(int64_t n) { return n < 0 ? -1 : stored_size(n) + 8; }
+int64_t nrqio_deflate_bound(int64_t n) { return n < 0 ? -1 : stored_size(n) + 16; }
 
 uint32_t nrqio_adler32(const uint8_t* src, int64_t n) { return adler32(src, n < 0 ? 0 : n); }
 

@@ -29,6 +29,7 @@ class ResquiggleParams:
     given_limits: bool = False
     big_region_cap: int = 16384
     exact_stats: bool = False            # event mean/sd in numpy's summation order (bit-identical, slower)
+    long_read_parts: int = 0             # nrq_params.long_read_parts (0: the host entry point decides per chunk)
     debug_flags: int = 0
 
     def to_c(self):
@@ -42,6 +43,7 @@ class ResquiggleParams:
         p.min_seg_len = int(self.min_event_obs)
         p.timeout_ns = 0 if self.timeout is None else int(self.timeout * 1e9)
         p.big_region_cap = int(self.big_region_cap)
+        p.long_read_parts = int(self.long_read_parts)
         p.debug_flags = int(self.debug_flags) | (2 if self.exact_stats else 0)
         return p
 

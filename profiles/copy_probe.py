@@ -22,6 +22,7 @@ def main():
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')  # stdout carries the JSON line only
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     h2d_bytes = int(float(os.environ.get('PROBE_H2D_GB', '1.92')) * 1e9)
     d2h_bytes = int(float(os.environ.get('PROBE_D2H_GB', '2.07')) * 1e9)
