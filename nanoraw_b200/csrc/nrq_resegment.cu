@@ -261,10 +261,27 @@ __device__ __forceinline__ int get_cpts(const SegCtx& c, int t0, int t_stop, int
     __syncwarp();
     const double* cs = buf + 1;
     int res;
+    // keys per lane by region size.  Every instantiation is a copy of the selection loop in a kernel whose
+    // instruction footprint matters (see drive_until_push): NRQ_SEG_ESET picks which sizes get their own
+#ifndef NRQ_SEG_ESET
+#define NRQ_SEG_ESET 1248
+#endif
+#if NRQ_SEG_ESET == 1248
     if (nrd <= 32) res = select_cpts_regs<1>(c, cs, nrd, K, t0, outpos, c.picks);
     else if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos, c.picks);
     else if (kRegionCap <= 135 || nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos, c.picks);
     else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos, c.picks);
+#elif NRQ_SEG_ESET == 248
+    if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos, c.picks);
+    else if (kRegionCap <= 135 || nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos, c.picks);
+    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos, c.picks);
+#elif NRQ_SEG_ESET == 28
+    if (nrd <= 64) res = select_cpts_regs<2>(c, cs, nrd, K, t0, outpos, c.picks);
+    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos, c.picks);
+#else
+    if (nrd <= 128) res = select_cpts_regs<4>(c, cs, nrd, K, t0, outpos, c.picks);
+    else res = select_cpts_regs<8>(c, cs, nrd, K, t0, outpos, c.picks);
+#endif
     __syncwarp();
     return res;
   }
@@ -311,14 +328,6 @@ __device__ __forceinline__ int search_group(SegCtx& c, int& lo, int hi, int& max
     st = swallow_previous(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
     if (st != NRQ_ST_OK) return st;
   }
-}
-
-// extend_and_join (:217-226) followed by extend_for_cpts (:256-276)
-__device__ __forceinline__ int close_group(SegCtx& c, int& lo, int hi, int& maxend, int& start, int& stop) {
-  int K, t_start, t_stop;  // t[start], t[stop] of the current (start, stop)
-  int st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
-  if (st != NRQ_ST_OK) return st;
-  return search_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
 }
 
 __device__ __forceinline__ long long global_ns() {
@@ -384,23 +393,40 @@ __device__ __forceinline__ void push_group(SegCtx& c, int start, int stop, int l
 
 // The driver loop of get_indel_groups (:286-314), indel by indel, from a group (lo .. hi, maxend) that is still
 // open and indel k as the next one to look at, until that group has been finished and pushed.  On return k is the
-// first indel of the next group (n_ind when the read's last group was pushed).  One call site of close_group and
-// one of this function: every inlined copy carries the whole change-point search with it.
-__device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend) {
+// first indel of the next group (n_ind when the read's last group was pushed).  `planned`: the group is complete
+// (the next indel does not touch it) and its extend_group result (p_start, p_stop, p_K) is at hand, as are
+// `known_none` searches K2a has already lost.  This is the ONE call site of the change-point search in the kernel:
+// every inlined copy carries the whole search with it, and with the first searches done by K2a the walk is control
+// flow spread over the whole kernel -- its instruction footprint is what the caches have to hold (r2c: 4.3
+// 'no instruction' stall cycles per issued instruction with two copies).
+__device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend, bool planned,
+                                                int p_start, int p_stop, int p_K, int known_none) {
   int start, stop;
   for (;;) {
     const bool more = k < c.n_ind;
     int4 nxt = make_int4(0, 0, 0, 0);
     if (more) {
       nxt = c.ind[k];
-      if (maxend >= nxt.x) {  // :291-292
+      if (!planned && maxend >= nxt.x) {  // :291-292
         hi = k++;
         maxend = max(maxend, nxt.y);
         continue;
       }
     }
-    int st = close_group(c, lo, hi, maxend, start, stop);  // :293-294, and :307-314 for the read's last group
+    // extend_and_join (:217-226) followed by extend_for_cpts (:256-276); :307-314 for the read's last group
+    int K, t_start, t_stop, st = NRQ_ST_OK;
+    if (planned) {
+      start = p_start; stop = p_stop; K = p_K;
+      t_start = c.t[start];
+      t_stop = c.t[stop];
+    } else {
+      st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
+      known_none = 0;
+    }
     if (st != NRQ_ST_OK) return st;
+    st = search_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop, known_none);
+    if (st != NRQ_ST_OK) return st;
+    planned = false;
     if (more && stop >= nxt.x) {  // :299-300
       hi = k++;
       maxend = max(maxend, nxt.y);
@@ -513,20 +539,23 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
         __syncwarp();
       }
     }
-    // ---- walk the planned groups; whatever cannot be taken from a plan goes indel by indel (one call site below)
-    int d_lo = k, d_hi = k, d_maxend = 0, d_k = k + 1;
-    if (drive) d_maxend = c.ind[k].y;
-    while (todo) {
+    // ---- the next group that is not finished yet: taken from its plan if there is one (a speculated find that is
+    // not clean, a speculated None, or no speculation at all), else indel by indel -- one call site below
+    bool go = drive, g_planned = false;
+    int g_lo = k, g_hi = k, g_maxend = 0, g_k = k + 1, g_start = 0, g_stop = 0, g_K = 0, g_known = 0;
+    if (drive) g_maxend = c.ind[k].y;
+    while (todo && !go) {
       const int s = __ffs(todo) - 1;
       todo &= todo - 1;
-      int lo = k + s;
+      const int lo = k + s;
       const int4 rec = c.groups[lo];
       const int hi = lo + ((rec.z >> kPlanKBits) & 31);
-      int st = (rec.z >> (kPlanKBits + 5)) & 15;
-      int start = rec.x, stop = rec.y, maxend = rec.w;
+      const int st = (rec.z >> (kPlanKBits + 5)) & 15;
+      int start = rec.x, stop = rec.y;
+      const int maxend = rec.w;
+      g_lo = lo; g_hi = hi; g_maxend = maxend; g_k = hi + 1;
       if (st == kPlanGeneric) {  // a plan that did not fit its record: same group, from scratch
-        drive = true;
-        d_lo = lo; d_hi = hi; d_maxend = maxend; d_k = hi + 1;
+        go = true;
         break;
       }
       if (st != NRQ_ST_OK) return st;
@@ -534,36 +563,38 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
       const int f_start = __shfl_sync(kFull, p_start, s), f_stop = __shfl_sync(kFull, p_stop, s);
       const int f_K = __shfl_sync(kFull, p_K, s);
       const bool found = (found_mask >> s) & 1u;
-      if (found && f_start > c.top_stop) {  // searched by K2a to the end, and no finished group in the way
-        start = f_start;
-        stop = f_stop;
-        const int t0 = c.t[start];
-        int32_t* o = c.out + start + c.ind[lo].w + 1;
-        const unsigned char* src = c.cpt_bytes + spec_offset(sp_y);
-        for (int i = lane; i < f_K; i += 32) o[i] = t0 + (int)src[i];
-      } else {
-        // searches K2a is known to have lost: all of a chain that ended in None, the retries before a find
-        const int known = found ? spec_retries(sp_y) : (((none_mask >> s) & 1u) ? spec_retries(sp_y) + 1 : 0);
-        st = search_group(c, lo, hi, maxend, start, stop, rec.z & ((1 << kPlanKBits) - 1), c.t[start], c.t[stop],
-                          known);
-        if (st != NRQ_ST_OK) return st;
+      if (!(found && f_start > c.top_stop)) {
+        // to be searched; searches K2a is known to have lost: all of a chain that ended in None, the retries
+        // before a find
+        go = g_planned = true;
+        g_start = start; g_stop = stop; g_K = rec.z & ((1 << kPlanKBits) - 1);
+        g_known = found ? spec_retries(sp_y) : (((none_mask >> s) & 1u) ? spec_retries(sp_y) + 1 : 0);
+        break;
       }
+      // searched by K2a to the end, and no finished group in the way (but it reaches the next indel, or it
+      // follows a group that was not clean)
+      start = f_start;
+      stop = f_stop;
+      const int t0 = c.t[start];
+      int32_t* o = c.out + start + c.ind[lo].w + 1;
+      const unsigned char* src = c.cpt_bytes + spec_offset(sp_y);
+      for (int i = lane; i < f_K; i += 32) o[i] = t0 + (int)src[i];
       if (hi + 1 < c.n_ind) {
         const int4 nxt = c.ind[hi + 1];
         if (stop >= nxt.x) {  // :299-300: the finished group reaches the next indel and stays open
-          drive = true;       // plans made behind this point may no longer hold
-          d_lo = lo; d_hi = hi + 1; d_maxend = max(maxend, nxt.y); d_k = hi + 2;
+          go = true;          // plans made behind this point may no longer hold
+          g_hi = hi + 1; g_maxend = max(maxend, nxt.y); g_k = hi + 2;
           break;
         }
       }
       push_group(c, start, stop, lo, maxend);
       next_k = hi + 1;
-      if (c.spec) break;  // plan again from here: whatever follows is most likely finished in one go as well
+      break;  // plan again from here: whatever follows is most likely finished in one go
     }
-    if (drive) {
-      int st = drive_until_push(c, d_k, d_lo, d_hi, d_maxend);
+    if (go) {
+      const int st = drive_until_push(c, g_k, g_lo, g_hi, g_maxend, g_planned, g_start, g_stop, g_K, g_known);
       if (st != NRQ_ST_OK) return st;
-      next_k = d_k;
+      next_k = g_k;
     }
     k = next_k;
   }

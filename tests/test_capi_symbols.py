@@ -45,13 +45,30 @@ def test_status_messages_match_reference_strings():
     assert _lib.status_message(_lib.ST_OK) == ''
 
 
-def test_params_struct_layout():
-    # must match struct nrq_params in include/nrq.h (natural alignment)
-    assert C.sizeof(_lib.NrqParams) == 48
-    assert _lib.NrqParams.outlier_thresh.offset == 8
-    assert _lib.NrqParams.timeout_ns.offset == 32
-    assert C.sizeof(_lib.NrqBatch) == 96
-    assert C.sizeof(_lib.NrqResults) == 88
+def test_params_struct_layout(tmp_path):
+    """the ctypes mirrors against the C compiler's view of include/nrq.h: size and every field offset"""
+    import re
+    import subprocess
+    assert C.sizeof(_lib.NrqParams) == 56 and _lib.NrqParams.timeout_ns.offset == 32
+    assert C.sizeof(_lib.NrqBatch) == 96 and C.sizeof(_lib.NrqResults) == 88
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    structs = {'nrq_params': _lib.NrqParams, 'nrq_batch': _lib.NrqBatch, 'nrq_results': _lib.NrqResults}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "nrq.h"', 'int main(void) {']
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    lines += ['return 0; }']
+    src = tmp_path / 'probe.c'
+    src.write_text('\n'.join(lines))
+    exe = tmp_path / 'probe'
+    subprocess.run(['gcc', '-I', os.path.join(root, 'include'), '-o', str(exe), str(src)], check=True)
+    out = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True, check=True)
+               .stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(out[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(out['%s.%s' % (cname, fname)]) == getattr(cls, fname).offset, (cname, fname)
 
 
 def test_engine_refuses_without_gpu():
