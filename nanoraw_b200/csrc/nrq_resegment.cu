@@ -360,21 +360,26 @@ __device__ int splice_and_validate(const SegCtx& c, int n_bases, int n_norm, int
       reg += c.t[grp.y] - c.t[grp.x];
     }
     const bool wide = to - from >= kLaneCopy;
-    if (!wide)
-      for (int j = from; j <= to; ++j) c.out[j + d] = c.t[j];
+    if (!wide) {  // loads first (read-only path, four in flight), then the stores: a lane's copy is latency, not work
+#pragma unroll 4
+      for (int j = from; j <= to; ++j) c.out[j + d] = __ldg(c.t + j);
+    }
     unsigned todo = __ballot_sync(kFull, wide);
     while (todo) {
       const int src = __ffs(todo) - 1;
       todo &= todo - 1;
       const int f = __shfl_sync(kFull, from, src), z = __shfl_sync(kFull, to, src), dd = __shfl_sync(kFull, d, src);
-      for (int j = f + (int)lane; j <= z; j += 32) c.out[j + dd] = c.t[j];
+#pragma unroll 4
+      for (int j = f + (int)lane; j <= z; j += 32) c.out[j + dd] = __ldg(c.t + j);
     }
   }
   region_samples += __reduce_add_sync(kFull, reg);
-  for (int j = (c.ng > 0 ? c.groups[c.ng - 1].y : 0) + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = c.t[j];
+#pragma unroll 4
+  for (int j = (c.ng > 0 ? c.groups[c.ng - 1].y : 0) + (int)lane; j <= c.last; j += 32) c.out[j + dtotal] = __ldg(c.t + j);
   __syncwarp();
   const int total = c.last + 1 + dtotal;
   int zero_len = 0;
+#pragma unroll 4
   for (int i = lane; i + 1 < total; i += 32) zero_len |= (c.out[i + 1] - c.out[i] < 1);
   zero_len = __any_sync(kFull, zero_len);
   if (zero_len) return NRQ_ST_ZERO_LEN;
@@ -400,16 +405,19 @@ __device__ __forceinline__ void push_group(SegCtx& c, int start, int stop, int l
 // flow spread over the whole kernel -- its instruction footprint is what the caches have to hold (r2c: 4.3
 // 'no instruction' stall cycles per issued instruction with two copies).
 __device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int hi, int maxend, bool planned,
-                                                int p_start, int p_stop, int p_K, int known_none) {
+                                                int p_start, int p_stop, int p_K, int p_t_start, int p_t_stop,
+                                                int p_nxt_x, int p_nxt_y, int known_none) {
   int start, stop;
   for (;;) {
     const bool more = k < c.n_ind;
-    int4 nxt = make_int4(0, 0, 0, 0);
-    if (more) {
-      nxt = c.ind[k];
-      if (!planned && maxend >= nxt.x) {  // :291-292
+    int nxt_x = p_nxt_x, nxt_y = p_nxt_y;  // (a planned group's next indel is in the planner's registers)
+    if (more && !planned) {
+      const int4 nxt = c.ind[k];
+      nxt_x = nxt.x;
+      nxt_y = nxt.y;
+      if (maxend >= nxt_x) {  // :291-292
         hi = k++;
-        maxend = max(maxend, nxt.y);
+        maxend = max(maxend, nxt_y);
         continue;
       }
     }
@@ -417,8 +425,8 @@ __device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int h
     int K, t_start, t_stop, st = NRQ_ST_OK;
     if (planned) {
       start = p_start; stop = p_stop; K = p_K;
-      t_start = c.t[start];
-      t_stop = c.t[stop];
+      t_start = p_t_start;
+      t_stop = p_t_stop;
     } else {
       st = extend_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop);
       known_none = 0;
@@ -427,9 +435,9 @@ __device__ __forceinline__ int drive_until_push(SegCtx& c, int& k, int lo, int h
     st = search_group(c, lo, hi, maxend, start, stop, K, t_start, t_stop, known_none);
     if (st != NRQ_ST_OK) return st;
     planned = false;
-    if (more && stop >= nxt.x) {  // :299-300
+    if (more && stop >= nxt_x) {  // :299-300
       hi = k++;
-      maxend = max(maxend, nxt.y);
+      maxend = max(maxend, nxt_y);
       continue;
     }
     push_group(c, start, stop, lo, maxend);  // :302-304
@@ -443,12 +451,11 @@ constexpr int kPlanKBits = 22;         // a record packs K (22 bits), the group'
 // get_indel_groups (:278-316).  The grouping of indels by touching padded spans (:291-292) and the first
 // extend_group of each group (:203-216) do not depend on how earlier groups fared, so they are worked out for the
 // next 32 indels at once, one lane per indel: a running maximum of the indel ends (warp scan) marks where groups
-// break, and the lane of each group's first indel grows the group until it can hold its change-points.  Each
-// finished plan is a 16-byte record parked in the read's group scratch at the index of the group's first indel
-// (the stack of finished groups never reaches that far: it holds at most one entry per consumed indel).  The warp
-// then walks the planned groups in order and does what the reference does for each: merge with finished groups it
-// runs into, search, retry; a group that ends up reaching the next indel (:299-300), or that does not fit the
-// 32-indel window, is carried on indel by indel (drive_until_push) and planning resumes behind it.
+// break, and the lane of each group's first indel grows the group until it can hold its change-points.  The plans
+// stay in those lanes' registers.  The leading groups that K2a has settled are finished at once; the first group
+// that is not goes through what the reference does for a group (merge with finished groups it runs into, search,
+// retry, carry on indel by indel if it ends up reaching the next indel (:299-300) or does not fit the 32-indel
+// window: drive_until_push), and planning resumes behind it.
 __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int n_norm, int& region_samples) {
   const int lane = (int)lane_id();
   const long long t_begin = timeout_ns > 0 ? global_ns() : 0;
@@ -477,20 +484,26 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     int2 spw = make_int2(0, 0);
     if (c.spec && valid) spw = c.spec[k + lane];
     bool sp_found = false, sp_none = false;
-    int p_start = 0, p_stop = 0, p_K = 0;  // this lane's plan, if it heads a planned group
+    // this lane's plan, if it heads a planned group: extend_group's result (q_*: start, stop, K, the boundaries
+    // t[start] / t[stop], a status) and where K2a's retries ended, if it found change-points (p_*).  The plans stay
+    // in the head lanes' registers; the walk below fetches one with shuffles.
+    int q_start = 0, q_stop = 0, q_K = 0, q_ts = 0, q_te = 0, q_st = NRQ_ST_OK;
+    int p_start = 0, p_stop = 0, p_K = 0;
     if (planned) {  // extend_group (:203-216) for the group lane .. e
       int start = my.x, stop = gmax, st = NRQ_ST_OK;
       int K = (zsum - my.w) + stop - start - 1;
       if (start < 0 || stop > c.last) st = NRQ_ST_BAD_ALIGNMENT;
       while (st == NRQ_ST_OK) {
-        if (c.t[stop] - c.t[start] >= (K + 2) * c.m) break;
+        q_ts = c.t[start];
+        q_te = c.t[stop];
+        if (q_te - q_ts >= (K + 2) * c.m) break;
         if (start == 0 && stop == c.last) { st = NRQ_ST_UNSATISFIABLE; break; }
         K += (start > 0) + (stop < c.last);
         start = max(0, start - 1);
         stop = min(c.last, stop + 1);
       }
       if (K < 0 || K >= (1 << kPlanKBits)) { st = kPlanGeneric; K = 0; }
-      c.groups[k + lane] = make_int4(start, stop, K | ((e - lane) << kPlanKBits) | (st << (kPlanKBits + 5)), gmax);
+      q_start = start; q_stop = stop; q_K = K; q_st = st;
       p_start = start; p_stop = stop; p_K = K;
       // K2a's result counts only if it started from this very plan
       if (st == NRQ_ST_OK && K >= 1 && K <= kSpecMaxK && stop - start <= 255 && e - lane <= kSpecMaxLen) {
@@ -511,9 +524,7 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     bool drive = todo == 0u;  // more than 32 indels in one group
     // ---- the leading planned groups that K2a has already searched successfully, that begin behind the group before
     // them (:220: no merge) and end before the next indel (:299: not left open) are finished as they stand: all of
-    // them at once, one lane per group (stack entry, change-points copied into their new_segs slots).  The stack
-    // entries land below the parked record of every group that is still to be walked (at most one finished group
-    // per consumed indel).
+    // them at once, one lane per group (stack entry, change-points copied into their new_segs slots).
     if (c.spec) {
       const unsigned before = todo & ((1u << lane) - 1u);
       const int prev_lane = before ? 31 - __clz(before) : 0;
@@ -529,7 +540,8 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
           const int t0 = c.t[p_start];
           int32_t* o = c.out + p_start + my.w + 1;
           const unsigned char* src = c.cpt_bytes + spec_offset(spw.y);
-          for (int i = 0; i < p_K; ++i) o[i] = t0 + (int)src[i];
+#pragma unroll 4
+          for (int i = 0; i < p_K; ++i) o[i] = t0 + (int)__ldg(src + i);
         }
         const int last_lane = 31 - __clz(prefix);
         c.ng += __popc(prefix);
@@ -544,21 +556,23 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
     bool go = drive, g_planned = false;
     int g_lo = k, g_hi = k, g_maxend = 0, g_k = k + 1, g_start = 0, g_stop = 0, g_K = 0, g_known = 0;
     if (drive) g_maxend = c.ind[k].y;
-    while (todo && !go) {
+    int g_ts = 0, g_te = 0, g_nx = 0, g_ny = 0;
+    if (todo && !go) {  // (one group per window goes this way: whatever follows is planned again)
       const int s = __ffs(todo) - 1;
-      todo &= todo - 1;
       const int lo = k + s;
-      const int4 rec = c.groups[lo];
-      const int hi = lo + ((rec.z >> kPlanKBits) & 31);
-      const int st = (rec.z >> (kPlanKBits + 5)) & 15;
-      int start = rec.x, stop = rec.y;
-      const int maxend = rec.w;
+      const int hi = k + __shfl_sync(kFull, e, s);
+      const int st = __shfl_sync(kFull, q_st, s);
+      int start = __shfl_sync(kFull, q_start, s), stop = __shfl_sync(kFull, q_stop, s);
+      const int maxend = __shfl_sync(kFull, gmax, s);
+      const int d_before = __shfl_sync(kFull, my.w, s);      // sum of the diffs of the indels before the group
+      const int nl = (hi + 1 - k) & 31;                      // the next indel sits in the window (group complete)
+      const int nxt_x = __shfl_sync(kFull, my.x, nl), nxt_y = __shfl_sync(kFull, my.y, nl);
       g_lo = lo; g_hi = hi; g_maxend = maxend; g_k = hi + 1;
-      if (st == kPlanGeneric) {  // a plan that did not fit its record: same group, from scratch
+      if (st == kPlanGeneric) {  // a K that does not fit the plan's fields: same group, from scratch
         go = true;
-        break;
-      }
-      if (st != NRQ_ST_OK) return st;
+      } else if (st != NRQ_ST_OK) {
+        return st;
+      } else {
       const int sp_y = __shfl_sync(kFull, spw.y, s);
       const int f_start = __shfl_sync(kFull, p_start, s), f_stop = __shfl_sync(kFull, p_stop, s);
       const int f_K = __shfl_sync(kFull, p_K, s);
@@ -567,32 +581,33 @@ __device__ int resegment_read(SegCtx& c, long long timeout_ns, int n_bases, int 
         // to be searched; searches K2a is known to have lost: all of a chain that ended in None, the retries
         // before a find
         go = g_planned = true;
-        g_start = start; g_stop = stop; g_K = rec.z & ((1 << kPlanKBits) - 1);
+        g_start = start; g_stop = stop; g_K = __shfl_sync(kFull, q_K, s);
+        g_ts = __shfl_sync(kFull, q_ts, s);
+        g_te = __shfl_sync(kFull, q_te, s);
+        g_nx = nxt_x; g_ny = nxt_y;
         g_known = found ? spec_retries(sp_y) : (((none_mask >> s) & 1u) ? spec_retries(sp_y) + 1 : 0);
-        break;
-      }
+      } else {
       // searched by K2a to the end, and no finished group in the way (but it reaches the next indel, or it
       // follows a group that was not clean)
       start = f_start;
       stop = f_stop;
       const int t0 = c.t[start];
-      int32_t* o = c.out + start + c.ind[lo].w + 1;
+      int32_t* o = c.out + start + d_before + 1;
       const unsigned char* src = c.cpt_bytes + spec_offset(sp_y);
       for (int i = lane; i < f_K; i += 32) o[i] = t0 + (int)src[i];
-      if (hi + 1 < c.n_ind) {
-        const int4 nxt = c.ind[hi + 1];
-        if (stop >= nxt.x) {  // :299-300: the finished group reaches the next indel and stays open
-          go = true;          // plans made behind this point may no longer hold
-          g_hi = hi + 1; g_maxend = max(maxend, nxt.y); g_k = hi + 2;
-          break;
-        }
+      if (hi + 1 < c.n_ind && stop >= nxt_x) {  // :299-300: the finished group reaches the next indel and stays open
+        go = true;                              // plans made behind this point may no longer hold
+        g_hi = hi + 1; g_maxend = max(maxend, nxt_y); g_k = hi + 2;
+      } else {
+        push_group(c, start, stop, lo, maxend);
+        next_k = hi + 1;
       }
-      push_group(c, start, stop, lo, maxend);
-      next_k = hi + 1;
-      break;  // plan again from here: whatever follows is most likely finished in one go
+      }
+      }
     }
     if (go) {
-      const int st = drive_until_push(c, g_k, g_lo, g_hi, g_maxend, g_planned, g_start, g_stop, g_K, g_known);
+      const int st = drive_until_push(c, g_k, g_lo, g_hi, g_maxend, g_planned, g_start, g_stop, g_K, g_ts, g_te,
+                                      g_nx, g_ny, g_known);
       if (st != NRQ_ST_OK) return st;
       next_k = g_k;
     }
