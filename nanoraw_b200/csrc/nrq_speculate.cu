@@ -134,7 +134,7 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
   const int nb_own = (nrd + 7) >> 3;  // this lane's key blocks
   const int col = act ? lane : 0;
   long long* slab = sm.slab[warp];       // key i of this lane at slab[i * L + col], i < 8 nb_max
-  long long* bmax = slab + nrd_max * L;  // largest key of block b at bmax[b * L + col]
+  int* bmaxh = reinterpret_cast<int*>(slab + nrd_max * L);  // largest high word of block b at bmaxh[b * L + col]
   unsigned* pick = sm.pick[warp];
   __syncwarp();  // the previous batch's columns are laid out differently
 #pragma unroll
@@ -201,40 +201,49 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
   }
 
   // ---- K rounds of arg-max over the lane's own keys: larger key first, larger index among equal keys (:244-254 under
-  // argsort(kind='stable')[::-1]); the pick's window i-3 .. i+4 is cleared (:249-250).  A round looks at the block
-  // maxima, then at the eight keys of the winning block, and brings the maxima of the (at most two) blocks the
-  // cleared window touches up to date.
-  auto block_max = [&](int b) {
-    const long long* q = slab + (8 * b) * L + col;
-    long long v = q[0];
+  // argsort(kind='stable')[::-1]); the pick's window i-3 .. i+4 is cleared (:249-250).  Per block of eight keys the
+  // slab also holds the largest HIGH WORD of its keys (a 32-bit maximum costs one instruction per key, a 64-bit one
+  // four): a round finds the largest high word over the blocks, then the exact arg-max among the keys of the
+  // block(s) that hold it -- nearly always one block, more only where keys of different blocks agree in their
+  // upper 32 bits -- and brings the maxima of the (at most two) blocks the cleared window touches up to date.
+  auto block_max_hi = [&](int b) {  // (little endian: the high word is the second int of a key; cleared key: -1)
+    const int* q = reinterpret_cast<const int*>(slab + (8 * b) * L + col) + 1;
+    int v = q[0];
 #pragma unroll
-    for (int u = 1; u < 8; ++u) v = max(v, q[u * L]);
+    for (int u = 1; u < 8; ++u) v = max(v, q[2 * u * L]);
     return v;
   };
   for (int b = 0; b < nb_max; ++b) {
-    long long v = -1ll;  // blocks beyond the lane's own region: nothing there
-    if (b < nb_own) v = block_max(b);
-    if (act) bmax[b * L + col] = v;
+    int v = -1;  // blocks beyond the lane's own region: nothing there
+    if (b < nb_own) v = block_max_hi(b);
+    if (act) bmaxh[b * L + col] = v;
   }
   const int Kmax = (int)__reduce_max_sync(kFull, (unsigned)K);
   bool fail = false;
   for (int round = 0; round < Kmax; ++round) {
     if (round < K && !fail) {
-      long long best = 0ll;  // every real key is >= 0, a cleared one is -1
-      int bb = -1;
-      const long long* q = bmax + col;
+      int best_hi = -1;      // every real key has a high word >= 0, a cleared one -1
+      unsigned tied = 0u;    // blocks whose maximum is best_hi
+      const int* q = bmaxh + col;
       for (int b = 0; b < nb_max; ++b, q += L) {
-        const long long v = q[0];
-        if (v >= best) { best = v; bb = b; }
+        const int h = q[0];
+        tied = h > best_hi ? 1u << b : (h == best_hi ? tied | (1u << b) : tied);
+        best_hi = max(best_hi, h);
       }
-      if (bb < 0) {
+      if (best_hi < 0) {
         fail = true;  // fewer than K placeable: None (:253-254)
       } else {
-        int bi = 8 * bb;
-        const long long* kq = slab + (8 * bb) * L + col;
+        long long best = -1ll;
+        int bi = 0;
+        for (unsigned tb = tied; tb; tb &= tb - 1u) {  // ascending blocks, ascending keys, '>=': the larger index wins
+          const int b = __ffs(tb) - 1;
+          const long long* kq = slab + (8 * b) * L + col;
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
-          if (kq[u * L] == best) bi = 8 * bb + u;
+          for (int u = 0; u < 8; ++u) {
+            const long long kv = kq[u * L];
+            if (kv >= best) { best = kv; bi = 8 * b + u; }
+          }
+        }
         pick[(bi >> 5) * 32 + lane] |= 1u << (bi & 31);
 #pragma unroll
         for (int d = -kSpecM + 1; d <= kSpecM; ++d) {
@@ -242,8 +251,8 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
           if ((unsigned)i < (unsigned)(8 * nb_own)) slab[i * L + col] = -1ll;
         }
         const int b_lo = max(bi - kSpecM + 1, 0) >> 3, b_hi = min(bi + kSpecM, 8 * nb_own - 1) >> 3;
-        bmax[b_lo * L + col] = block_max(b_lo);
-        if (b_hi != b_lo) bmax[b_hi * L + col] = block_max(b_hi);
+        bmaxh[b_lo * L + col] = block_max_hi(b_lo);
+        if (b_hi != b_lo) bmaxh[b_hi * L + col] = block_max_hi(b_hi);
       }
     }
     if (!__any_sync(kFull, round + 1 < K && !fail)) break;
@@ -387,8 +396,8 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         if (tid == 0) { sm.cursor = 0; sm.n_retry = 0; }
         __syncthreads();
         for (;;) {
-          // the next L tasks in sorted order: as many as the warp's slab holds (keys in blocks of 8 + a maximum per
-          // block, for the largest region among them)
+          // the next L tasks in sorted order: as many as the warp's slab holds (keys in blocks of 8 + a 32-bit maximum
+          // per block, for the largest region among them)
           int i0 = 0, L = 0;
           for (;;) {
             if (lane == 0) i0 = *reinterpret_cast<volatile int*>(&sm.cursor);
@@ -402,7 +411,9 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
               const int u = __shfl_up_sync(kFull, pm, o);
               if (lane >= o) pm = max(pm, u);
             }
-            const bool fits = i0 + lane < nt && (lane + 1) * 9 * ((pm + 7) >> 3) <= kSpecSlab;
+            // per lane: 8 keys and half a key's worth of block maximum for every block of the largest region
+            const int nbp = (pm + 7) >> 3;
+            const bool fits = i0 + lane < nt && (lane + 1) * (8 * nbp + ((nbp + 1) >> 1)) <= kSpecSlab;
             L = __popc(__ballot_sync(kFull, fits));  // a prefix of the lanes: the need only grows with the lane
             int won = 0;
             if (lane == 0) won = atomicCAS(&sm.cursor, i0, i0 + L) == i0;

@@ -374,6 +374,12 @@ class ResquiggleEngine(object):
         given.  -> (status, [(group_start, group_stop, cpts, indels)]) with indels as (start, end, diff)."""
         t = self.torch
         sig = np.ascontiguousarray(norm_signal, dtype=np.float64)
+        align_segs = np.asarray(align_segs)
+        if len(align_segs) and int(align_segs[-1]) > len(sig):
+            # the reference slices raw_signal[a:b] and would silently run on a truncated region; the kernel indexes
+            # the signal directly, so a signal shorter than the last boundary is refused up front with the message
+            # resquiggle_read gives for it (resquiggle.py:379-381)
+            return _lib.ST_PAST_END, []
         batch = ReadBatch.from_arrays([np.zeros(1, np.int16)], [0], [align_segs], [read_align],
                                       [genome_align])
         batch.norm_signal = sig

@@ -238,3 +238,81 @@ def test_running_difference_trace():
         got = rsq.running_differences(window)
         want = orc.running_diffs(window) if width >= 8 else np.zeros(0)
         assert np.array_equal(got, want)
+
+
+def test_native_front_end_feeds_the_device_batch():
+    """f-2 through the C ABI end to end: SAM records and basecall events go through libnrqio
+    (nrqio_events_to_starts, nrqio_frontend_batch), whose CSR arrays are handed to nrq_resquiggle_batch_host as they
+    are; the result must equal what the per-read Python front end + engine.run give"""
+    import ctypes as C
+    from nanoraw_b200 import _lib, _libio, frontend, synth
+    from nanoraw_b200.batch import ReadBatch
+    from nanoraw_b200.engine import ResquiggleEngine, ResquiggleParams
+    engine = ResquiggleEngine()
+    genome = synth.make_genome(300_000, seed=12)
+    contig = genome.tobytes()
+    cfg = synth.SynthConfig(span_mean=500, span_sd=60, seed_base=66000)
+    reads = synth.make_reads(10, cfg, genome=genome)
+    fe = (_libio.FeRead * len(reads))()
+    keep, starts_in, raws = [], [], []
+    for i, rd in enumerate(reads):
+        clip = (7 + i, 3 + 2 * i)
+        ev = synth.to_basecall_events(rd, stay_rate=0.15, clip_bases=clip, seed=i)
+        st, starts, bases, read_start = _libio.events_to_starts(ev, True, 4000, 0)
+        assert st == _libio.FE_OK
+        rec = synth.to_sam_record(rd, soft_clip=clip, seed=i)
+        cig, seq = rec['cigar'].encode(), rec['seq'].encode()
+        keep += [cig, seq, starts]
+        fe[i].cigar, fe[i].flag, fe[i].pos = cig, int(rec['flag']), int(rec['pos'])
+        fe[i].seq, fe[i].seq_len = seq, len(seq)
+        fe[i].contig, fe[i].contig_len = contig, len(contig)
+        fe[i].starts, fe[i].n_starts, fe[i].read_start = starts.ctypes.data, len(starts), read_start
+        starts_in.append(starts)
+        raws.append(rd.raw)
+    R = len(reads)
+    cap_s = sum(len(s) for s in starts_in)
+    cap_a = 3 * cap_s
+    status = np.zeros(R, np.int32); read_start = np.zeros(R, np.int32)
+    starts = np.zeros(cap_s, np.int32); starts_off = np.zeros(R + 1, np.int64)
+    ra = np.zeros(cap_a, np.uint8); ga = np.zeros(cap_a, np.uint8); align_off = np.zeros(R + 1, np.int64)
+    clips = np.zeros(2 * R, np.int64); tallies = np.zeros(4 * R, np.int64)
+    rc = _libio.load().nrqio_frontend_batch(fe, R, 4, status.ctypes.data, read_start.ctypes.data, starts.ctypes.data,
+                                            cap_s, starts_off.ctypes.data, ra.ctypes.data, ga.ctypes.data, cap_a,
+                                            align_off.ctypes.data, clips.ctypes.data, tallies.ctypes.data)
+    assert rc == 0 and (status == 0).all()
+    # the same reads through the Python objects
+    want_reads = []
+    for i, rd in enumerate(reads):
+        want_reads.append(synth.SynthRead(
+            raw=rd.raw, read_start_rel_to_raw=int(read_start[i]),
+            starts=starts[starts_off[i]:starts_off[i + 1]].astype(np.int64),
+            read_align=ra[align_off[i]:align_off[i + 1]].tobytes(),
+            genome_align=ga[align_off[i]:align_off[i + 1]].tobytes()))
+        assert want_reads[-1].read_align == rd.read_align and want_reads[-1].genome_align == rd.genome_align
+        assert np.array_equal(want_reads[-1].starts, rd.starts)
+    want = engine.run(ReadBatch.from_reads(want_reads), ResquiggleParams())
+    # ... and the CSR arrays as libnrqio left them, straight into the host entry point
+    raw = np.concatenate(raws).astype(np.int16)
+    raw_off = np.concatenate([[0], np.cumsum([len(r) for r in raws])]).astype(np.int64)
+    A = int(align_off[-1])
+    hb = _lib.NrqBatch()
+    hb.n_reads = R
+    for name, arr in (('raw', raw), ('raw_off', raw_off), ('read_start', read_start), ('starts', starts),
+                      ('starts_off', starts_off), ('read_align', ra), ('genome_align', ga), ('align_off', align_off)):
+        setattr(hb, name, arr.ctypes.data)
+    outs = {'status': np.zeros(R, np.int32), 'n_bases': np.zeros(R, np.int32), 'scale_values': np.zeros(4 * R),
+            'new_segs': np.zeros(A + R, np.int32), 'norm_mean': np.zeros(A), 'norm_stdev': np.zeros(A),
+            'ev_length': np.zeros(A, np.uint32), 'ev_base': np.zeros(A, np.uint8)}
+    hr = _lib.NrqResults()
+    for k, v in outs.items():
+        setattr(hr, k, v.ctypes.data)
+    pc = ResquiggleParams().to_c()
+    h = engine.lib.nrq_create(engine.device.index or 0)
+    _lib.check(engine.lib.nrq_resquiggle_batch_host(h, C.byref(hb), C.byref(pc), C.byref(hr)), 'host batch')
+    engine.lib.nrq_destroy(h)
+    assert np.array_equal(outs['status'], want.status) and np.array_equal(outs['n_bases'], want.n_bases)
+    for r in range(R):
+        o, n = int(align_off[r]), int(want.n_bases[r])
+        assert np.array_equal(outs['new_segs'][o + r:o + r + n + 1], want.new_segs_of(r))
+        assert np.array_equal(outs['norm_mean'][o:o + n], want.norm_mean[o:o + n])
+        assert np.array_equal(outs['ev_length'][o:o + n], want.ev_length[o:o + n])
