@@ -415,6 +415,8 @@ def gpu_arm(args):
     if args.fast5_files > 0:
         if world > 1:
             os.environ['NRQ_IO_PROCS'] = str(max(2, host_cores() // world))
+            os.environ.setdefault('NRQ_F5_THREADS', str(max(2, host_cores() // world)))
+            os.environ.setdefault('NRQ_PACK_THREADS', str(max(2, min(16, host_cores() // world))))
             # the host cores are shared by all ranks: fewer files per rank keep the leg's duration about the same
             from nanoraw_b200 import resquiggle as _rsq
             args.fast5_files = max(2 * _rsq.DEVICE_BATCH_READS, args.fast5_files // world)
@@ -559,6 +561,11 @@ def e2e_leg(args, lib, _lib, host_batch, pc, device_index, barrier):
     return samples, e2e_ms, h2d, d2h
 
 
+def _libio_threads():
+    from nanoraw_b200 import _libio
+    return _libio.f5_threads()
+
+
 def fast5_leg(args, reads, barrier=None):
     """The re-squiggle worker's whole body (resquiggle.py:403-440 -> 318-401) on FAST5 files on disk: open each
     file and read its raw signal, one device batch through the C ABI, RawGenomeCorrected written back into each
@@ -612,10 +619,11 @@ def fast5_leg(args, reads, barrier=None):
                 'failed_reads': len(failed), 'seconds': dt, 'io_procs': fast5_jobs.io_procs(),
                 'bytes_per_file_in': int(np.mean(sizes)), 'events_rows_file0': int(len(ev)),
                 'setup_seconds': setup_s,
-                'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal read, device '
-                        'batch, datasets packed into gzip chunks by libnrqio threads, RawGenomeCorrected '
-                        'write-back into the same file (hdf5_min.py); mapper and basecall event parsing not '
-                        'included'}
+                'f5_threads': _libio_threads(),
+                'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal inflated '
+                        'into pinned staging (libnrqio threads), device batch, datasets packed into gzip chunks and '
+                        'the RawGenomeCorrected group appended to the same file (libnrqio threads; hdf5_min.py '
+                        'for files outside its HDF5 slice); mapper and basecall event parsing not included'}
     finally:
         fast5_jobs.shutdown()
         shutil.rmtree(tmp, ignore_errors=True)

@@ -114,6 +114,67 @@ int nrqio_frontend_batch(const nrqio_fe_read* reads, int32_t n_reads, int32_t n_
                          uint8_t* read_align, uint8_t* genome_align, int64_t align_cap, int64_t* align_off,
                          int64_t* clip, int64_t* tallies);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * FAST5 files without libhdf5: the two things the re-squiggle worker does to a file,
+ * for whole device batches on n_threads threads, straight from / into the arrays of the C ABI above.
+ *   read   /Raw/Reads/<the read>/Signal and the channel_id attributes          (nanoraw/resquiggle.py:327-347)
+ *   write  /Analyses/<corrected group>/<subgroup> with its attributes, Alignment/{read_alignment, genome_alignment,
+ *          read_segments} and Events                                            (nanoraw/resquiggle.py:80-135)
+ * On-disk forms read: superblock 0-3, object headers v1 / v2, symbol-table groups and compact link messages,
+ * compact / contiguous / chunked int16 signals (v1 B-tree or single chunk; deflate, shuffle, fletcher32).  The write
+ * appends to files with a version 0 / 1 superblock whose <corrected group> is a symbol-table group (what libhdf5
+ * writes by default and what nanoraw_b200/hdf5_min.py writes), in the forms hdf5_min.py uses.  Per-file outcomes are
+ * status codes; on NRQIO_F5_UNSUPPORTED (a valid file outside this slice) the caller takes the Python reader /
+ * writer, which handles more forms, for that file.
+ * ------------------------------------------------------------------------------------------------------------ */
+enum {
+  NRQIO_F5_OK = 0,
+  NRQIO_F5_IO = 1,          /* cannot open / read / write the file */
+  NRQIO_F5_FORMAT = 2,      /* not an HDF5 file, or damaged */
+  NRQIO_F5_UNSUPPORTED = 3, /* valid HDF5 outside the slice implemented here */
+  NRQIO_F5_MISSING = 4,     /* a group, dataset or attribute the worker needs is not in the file */
+  NRQIO_F5_EXISTS = 5       /* <subgroup> is already there (h5py's create_group raises) */
+};
+
+typedef struct nrqio_f5_batch nrqio_f5_batch;
+
+/* Opens the n files strtab + path_off[i] (NUL-terminated names), finds each raw signal and fills n_samples[i],
+ * status[i] and channel[4 i ..] = offset, range, digitisation, sampling_rate (channel may be NULL).  The file images
+ * stay in *out until nrqio_f5_read_raw_batch has inflated them.  Returns 0, or -1 on a bad argument. */
+int nrqio_f5_open_raw_batch(const char* strtab, const int64_t* path_off, int32_t n, int32_t n_threads,
+                            nrqio_f5_batch** out, int64_t* n_samples, double* channel, int32_t* status);
+/* Signal of file i -> dst[dst_off[i] .. dst_off[i] + n_samples[i]) (e.g. nrq_batch.raw in pinned memory);
+ * dst_off[i] < 0 skips the file.  status[i] as above. */
+int nrqio_f5_read_raw_batch(nrqio_f5_batch* h, int16_t* dst, const int64_t* dst_off, int32_t n_threads,
+                            int32_t* status);
+void nrqio_f5_close_batch(nrqio_f5_batch* h);
+
+/* The corrected reads of one result batch, as nrqio_pack_corrected left them. */
+typedef struct nrqio_f5_corrected_batch {
+  int32_t n;
+  int32_t outlier_is_int;       /* outlier_threshold is written as int64 (else float64) */
+  const char* corrected_group;  /* e.g. "RawGenomeCorrected_000": exists under /Analyses (prep_fast5, :942-988) */
+  const char* subgroup;         /* e.g. "BaseCalled_template": created */
+  const char* norm_type;
+  double outlier_threshold;
+  const char* strtab;           /* NUL-terminated strings the three offset arrays point into */
+  const int64_t* path_off;      /* [n] file names */
+  const int64_t* chrom_off;     /* [n] mapped_chrom */
+  const int64_t* strand_off;    /* [n] mapped_strand */
+  const double* scale_values;   /* [4 n] shift, scale, lower_lim, upper_lim */
+  const int64_t* ints;          /* [8 n] mapped_start, clipped_bases_start, clipped_bases_end, num_insertions,
+                                   num_deletions, num_matches, num_mismatches, read_start_rel_to_raw */
+  const int32_t* n_bases;       /* [n] rows of Events */
+  const int64_t* n_align;       /* [n] columns of the alignment */
+  const int64_t* n_segs;        /* [n] entries of read_segments */
+  const uint8_t* chunks;        /* nrqio_pack_corrected: out, chunk_off, chunk_len (4 per read) */
+  const int64_t* chunk_off;
+  const int64_t* chunk_len;
+  const int32_t* skip;          /* [n] or NULL: nonzero = leave this file alone */
+} nrqio_f5_corrected_batch;
+/* Appends the group of every read to its file; status[i] as above.  Returns 0, or -1 on a bad argument. */
+int nrqio_f5_write_corrected_batch(const nrqio_f5_corrected_batch* w, int32_t n_threads, int32_t* status);
+
 #ifdef __cplusplus
 }
 #endif

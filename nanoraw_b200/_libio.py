@@ -33,6 +33,26 @@ SYMBOLS.update({
                                        _P, _P]),
 })
 
+
+
+class F5CorrectedBatch(C.Structure):
+    """nrqio_f5_corrected_batch"""
+    _fields_ = [('n', C.c_int32), ('outlier_is_int', C.c_int32), ('corrected_group', C.c_char_p),
+                ('subgroup', C.c_char_p), ('norm_type', C.c_char_p), ('outlier_threshold', C.c_double),
+                ('strtab', _P), ('path_off', _P), ('chrom_off', _P), ('strand_off', _P), ('scale_values', _P),
+                ('ints', _P), ('n_bases', _P), ('n_align', _P), ('n_segs', _P), ('chunks', _P), ('chunk_off', _P),
+                ('chunk_len', _P), ('skip', _P)]
+
+
+SYMBOLS.update({
+    'nrqio_f5_open_raw_batch': (C.c_int, [_P, _P, C.c_int32, C.c_int32, C.POINTER(_P), _P, _P, _P]),
+    'nrqio_f5_read_raw_batch': (C.c_int, [_P, _P, _P, C.c_int32, _P]),
+    'nrqio_f5_close_batch': (None, [_P]),
+    'nrqio_f5_write_corrected_batch': (C.c_int, [C.POINTER(F5CorrectedBatch), C.c_int32, _P]),
+})
+
+F5_OK, F5_IO, F5_FORMAT, F5_UNSUPPORTED, F5_MISSING, F5_EXISTS = range(6)
+
 FE_OK, FE_EVENTS_BEFORE_RAW, FE_TOO_FEW_SEGMENTS, FE_ZERO_LENGTH, FE_ALL_STAYS, FE_BAD_CIGAR, \
     FE_SEQ_CIGAR_DISAGREE, FE_CAPACITY, FE_BAD_INPUT = range(9)
 
@@ -155,3 +175,121 @@ def sam_to_rows(cigar, flag, pos, seq, contig):
                                tallies.ctypes.data)
     k = n_cols.value
     return st, rr[:k].tobytes(), gr[:k].tobytes(), (int(clip[0]), int(clip[1])), tallies
+
+
+# ---------------------------------------------------------------------------------------------- FAST5 files
+def f5_threads():
+    """threads of the batch file functions (NRQ_F5_THREADS; default: the host cores, at most 32)"""
+    env = os.environ.get('NRQ_F5_THREADS')
+    if env is not None:
+        return max(1, int(env))
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        cores = os.cpu_count() or 1
+    return max(1, min(32, cores))
+
+
+def _strtab(strings):
+    """list of str / bytes -> (uint8 array of NUL-terminated strings, int64 offsets)"""
+    raw = [x if isinstance(x, bytes) else os.fsencode(x) if isinstance(x, os.PathLike) else str(x).encode('utf-8')
+           for x in strings]
+    off = np.zeros(len(raw), dtype=np.int64)
+    if raw:
+        np.cumsum([len(x) + 1 for x in raw[:-1]], out=off[1:])
+    tab = np.frombuffer(b'\x00'.join(raw) + b'\x00', dtype=np.uint8)
+    return tab, off
+
+
+class F5RawBatch(object):
+    """nrqio_f5_open_raw_batch over a list of file names: `n_samples`, `channel` (offset, range, digitisation,
+    sampling_rate per file) and `status` are known at once; `read_into` inflates the signals into a caller's
+    int16 array (pinned staging); `close` drops the file images."""
+
+    def __init__(self, paths, threads=None):
+        lib = load()
+        n = len(paths)
+        self.n = n
+        self.threads = f5_threads() if threads is None else int(threads)
+        self.n_samples = np.zeros(max(n, 1), dtype=np.int64)[:n]
+        self.channel = np.full((max(n, 1), 4), np.nan, dtype=np.float64)[:n]
+        self.status = np.zeros(max(n, 1), dtype=np.int32)[:n]
+        self._h = _P()
+        tab, off = _strtab(paths)
+        rc = lib.nrqio_f5_open_raw_batch(tab.ctypes.data, off.ctypes.data, n, self.threads, C.byref(self._h),
+                                         self.n_samples.ctypes.data, self.channel.ctypes.data,
+                                         self.status.ctypes.data)
+        if rc != 0:
+            raise _lib.NrqError('nrqio_f5_open_raw_batch failed')
+
+    def read_into(self, dst, dst_off):
+        """signals -> dst[dst_off[i] : dst_off[i] + n_samples[i]] (dst_off[i] < 0: skipped); -> status int32[n]"""
+        if dst.dtype != np.int16 or not dst.flags['C_CONTIGUOUS']:
+            raise ValueError('dst must be a contiguous int16 array')
+        dst_off = np.ascontiguousarray(dst_off, dtype=np.int64)
+        ok = (self.status == F5_OK) & (dst_off >= 0)
+        if ok.any() and int((dst_off[ok] + self.n_samples[ok]).max()) > dst.size:
+            raise ValueError('dst is too small')
+        status = np.zeros(max(self.n, 1), dtype=np.int32)[:self.n]
+        rc = load().nrqio_f5_read_raw_batch(self._h, dst.ctypes.data, dst_off.ctypes.data, self.threads,
+                                            status.ctypes.data)
+        if rc != 0:
+            raise _lib.NrqError('nrqio_f5_read_raw_batch failed')
+        return status
+
+    def close(self):
+        if self._h:
+            load().nrqio_f5_close_batch(self._h)
+            self._h = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
+def f5_write_corrected(paths, corrected_group, subgroup, norm_type, outlier_thresh, chroms, strands, scale_values,
+                       ints, n_bases, n_align, n_segs, chunks, chunk_off, chunk_len, skip=None, threads=None):
+    """nrqio_f5_write_corrected_batch: RawGenomeCorrected groups appended to their files -> status int32[n].
+    scale_values float64[n, 4]; ints int64[n, 8] (mapped_start, clipped_bases_start, clipped_bases_end,
+    num_insertions, num_deletions, num_matches, num_mismatches, read_start_rel_to_raw); chunks / chunk_off /
+    chunk_len as pack_corrected returns them."""
+    lib = load()
+    n = len(paths)
+    tab, offs = _strtab(list(paths) + list(chroms) + list(strands))
+    keep = [tab, offs]
+
+    def arr(a, dt, count):
+        a = np.ascontiguousarray(a, dtype=dt).reshape(-1)
+        if a.size < count:
+            raise ValueError('array too short')
+        keep.append(a)
+        return a.ctypes.data
+
+    w = F5CorrectedBatch()
+    w.n = n
+    w.outlier_is_int = int(isinstance(outlier_thresh, (int, np.integer)) and not isinstance(outlier_thresh, bool))
+    w.corrected_group = corrected_group.encode()
+    w.subgroup = subgroup.encode()
+    w.norm_type = norm_type.encode()
+    w.outlier_threshold = float(outlier_thresh)
+    w.strtab = tab.ctypes.data
+    w.path_off = arr(offs[:n], np.int64, n)
+    w.chrom_off = arr(offs[n:2 * n], np.int64, n)
+    w.strand_off = arr(offs[2 * n:3 * n], np.int64, n)
+    w.scale_values = arr(scale_values, np.float64, 4 * n)
+    w.ints = arr(ints, np.int64, 8 * n)
+    w.n_bases = arr(n_bases, np.int32, n)
+    w.n_align = arr(n_align, np.int64, n)
+    w.n_segs = arr(n_segs, np.int64, n)
+    w.chunks = chunks.ctypes.data
+    w.chunk_off = arr(chunk_off, np.int64, 4 * n)
+    w.chunk_len = arr(chunk_len, np.int64, 4 * n)
+    w.skip = arr(skip, np.int32, n) if skip is not None else None
+    status = np.zeros(max(n, 1), dtype=np.int32)[:n]
+    rc = lib.nrqio_f5_write_corrected_batch(C.byref(w), f5_threads() if threads is None else int(threads),
+                                            status.ctypes.data)
+    if rc != 0:
+        raise _lib.NrqError('nrqio_f5_write_corrected_batch failed')
+    return status

@@ -237,5 +237,44 @@ class PinnedBatcher(object):
         self.n_reads = r + 1
         return r
 
+    def fill(self, raw_lens, read_starts, starts_list, read_rows, genome_rows, given=None):
+        """A whole batch at once, the raw signals left for the caller to write: replaces what the batcher holds by R
+        reads with raw_lens[i] samples each and returns raw_off (int64[R + 1]); self.raw[raw_off[i]:raw_off[i + 1]]
+        is read i's signal (libnrqio inflates FAST5 signals straight into it).  Rows are bytes; `given`: None or
+        R pairs (shift, scale).  The caller has checked what `add` checks per read."""
+        R = len(raw_lens)
+        self.reset()
+        if R > self.max_reads:
+            self._grow_reads(R)
+        raw_off = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(np.asarray(raw_lens, dtype=np.int64), out=raw_off[1:])
+        st_off = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(s) for s in starts_list), dtype=np.int64, count=R), out=st_off[1:])
+        al_off = np.zeros(R + 1, dtype=np.int64)
+        np.cumsum(np.fromiter((len(s) for s in read_rows), dtype=np.int64, count=R), out=al_off[1:])
+        n_raw, n_st, n_al = int(raw_off[R]), int(st_off[R]), int(al_off[R])
+        if n_raw > self._cap['raw']:
+            self._grow('raw', n_raw)
+        if n_st > self._cap['starts']:
+            self._grow('starts', n_st)
+        if n_al > self._cap['align']:
+            self._grow('align', n_al)
+        if R:
+            self.starts[:n_st] = np.concatenate([np.asarray(s) for s in starts_list])
+            self.read_align[:n_al] = np.frombuffer(b''.join(read_rows), dtype=np.uint8)
+            self.genome_align[:n_al] = np.frombuffer(b''.join(genome_rows), dtype=np.uint8)
+            self.read_start[:R] = np.asarray(read_starts, dtype=np.int64)
+        self.raw_off[:R + 1] = raw_off
+        self.starts_off[:R + 1] = st_off
+        self.align_off[:R + 1] = al_off
+        if given is not None and R:
+            sv = self.scale_values_in[:4 * R].reshape(R, 4)
+            sv[:, :2] = np.asarray(given, dtype=np.float64).reshape(R, 2)
+            sv[:, 2:] = np.nan
+            self.has_given = True
+        self._n_raw, self._n_starts, self._n_align = n_raw, n_st, n_al
+        self.n_reads = R
+        return raw_off
+
     def input_bytes(self):
         return 2 * self._n_raw + 4 * self._n_starts + 2 * self._n_align + 28 * self.n_reads

@@ -24,16 +24,16 @@ def _stale():
 
 
 IO_LIB = os.path.join(PKG, 'libnrqio.so')
-IO_SOURCES = ['nrq_io.cpp', os.path.join('..', '..', 'include', 'nrq_io.h'), os.path.join('..', '..', 'include', 'nrq.h')]
+IO_SOURCES = ['nrq_io.cpp', 'nrq_fast5.cpp', os.path.join('..', '..', 'include', 'nrq_io.h'), os.path.join('..', '..', 'include', 'nrq.h')]
 
 
 def build_io(force=False, verbose=False):
-    """libnrqio.so: host-side C++ (deflate + chunk packing of the FAST5 write-back); g++, no CUDA"""
+    """libnrqio.so: host-side C++ (deflate + chunk packing of the FAST5 write-back, front end, FAST5 files); g++, no CUDA"""
     if not force and os.path.exists(IO_LIB) and all(
             os.path.getmtime(os.path.join(HERE, s)) <= os.path.getmtime(IO_LIB) for s in IO_SOURCES):
         return IO_LIB
     cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-shared', '-fPIC', '-pthread', '-o', IO_LIB,
-           os.path.join(HERE, 'nrq_io.cpp')]
+           os.path.join(HERE, 'nrq_io.cpp'), os.path.join(HERE, 'nrq_fast5.cpp'), '-lz']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

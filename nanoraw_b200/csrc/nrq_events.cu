@@ -515,10 +515,13 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         // sums carried in from earlier steps for the base that ends at the first boundary of this round
         const long long c1 = run1 - prev1;
         const unsigned long long c2 = run2 - prev2;
+        // the 32-bit rounds below work modulo 2^32, so the carried sums may also be "negative": in the second round
+        // of a step the last resolved boundary lies inside the step, ahead of the running prefix (|c2| < 2^30 then)
+        const bool c_small = ((c2 + (1ull << 30)) >> 31) == 0ull;
         // ---- round of a step with clipped samples (one step in eight): bases 1 .. nb - 2 only, carried sums fit 32
         // bits; the clipped samples of each base are differences of the packed (below, above) counter prefixes, and
         // only a base that holds one takes the general statistics
-        if (anyc && cur >= 2 && cur + 32 < nb && (c2 >> 30) == 0ull) {
+        if (anyc && cur >= 2 && cur + 32 < nb && c_small) {
           const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][(sl & 7) >> 2][t][sl & 3];
           const unsigned pEC = __shfl_up_sync(0xffffffffu, EC, 1);
           int nl = (int)(EC & 0xffffu), nh = (int)(EC >> 16);
@@ -568,7 +571,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           continue;
         }
         // ---- common round: no clipped sample in play, bases 1 .. nb - 2 only, carried sums fit 32 bits
-        if (!anyc && cur >= 2 && cur + 32 < nb && (c2 >> 30) == 0ull && runl == prevl && runh == prevh) {
+        if (!anyc && cur >= 2 && cur + 32 < nb && c_small && runl == prevl && runh == prevh) {
           if (lane == 0) { pE1 = -(int)c1; pE2 = 0u - (unsigned)c2; bpos = prevpos; }
           if (inb) {
             const int n = pos - bpos;

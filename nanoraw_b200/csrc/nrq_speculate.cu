@@ -446,6 +446,11 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
       if (valid) {
         my = ind[idx];
         sp[idx] = make_int2(0, 0);  // "not speculated" unless a task of this launch says otherwise
+        // planning is a chain of trips to memory (records, then the boundaries extend_group compares): the
+        // boundaries around this indel and the records of the next tile start their trip now
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t + max(my.x - 1, 0)));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(t + min(my.y + 1, last)));
+        if (idx + kSpecThreads < n_ind) asm volatile("prefetch.global.L1 [%0];" ::"l"(ind + idx + kSpecThreads));
       }
       int M = my.y;
 #pragma unroll

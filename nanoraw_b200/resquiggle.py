@@ -212,12 +212,43 @@ def _read_raw_inputs(fast5_fn, norm_type, basecall_group, subgroup):
 _BATCHER = []
 
 
-def _batcher():
-    """the worker process's pinned staging buffers (grow-only, reused for every device batch)"""
-    if not _BATCHER:
-        from .batch import PinnedBatcher
+def _batcher(which=0):
+    """the worker process's pinned staging buffers (grow-only, reused for every device batch).  The native FAST5
+    path fills batch n + 1 while batch n is on the device, so it alternates between two of them."""
+    from .batch import PinnedBatcher
+    while len(_BATCHER) <= which:
         _BATCHER.append(PinnedBatcher(max_reads=DEVICE_BATCH_READS))
-    return _BATCHER[0]
+    return _BATCHER[which]
+
+
+_IO_THREAD = []
+
+
+def _io_thread():
+    """one background thread per worker process: it sits in libnrqio's batch file functions (which run on their own
+    threads and hold no GIL) while the main thread drives the device"""
+    if not _IO_THREAD:
+        from concurrent.futures import ThreadPoolExecutor
+        _IO_THREAD.append(ThreadPoolExecutor(max_workers=2, thread_name_prefix='nrq-fast5'))
+    return _IO_THREAD[0]
+
+
+class _Later(object):
+    """results of a background call, read like the iterators fast5_jobs.start_jobs returns"""
+
+    def __init__(self, future):
+        self._future = future
+
+    def __iter__(self):
+        return iter(self._future.result())
+
+
+class _LoadedBatch(object):
+    """a device batch whose inputs libnrqio has put into a PinnedBatcher (BatchPipeline._load_native)"""
+    __slots__ = ('ready', 'failed', 'unreadable', 'batcher')
+
+    def __init__(self, ready, failed, unreadable, batcher):
+        self.ready, self.failed, self.unreadable, self.batcher = ready, failed, unreadable, batcher
 
 
 class _PendingRead(object):
@@ -250,17 +281,100 @@ class BatchPipeline(object):
         self.min_event_obs, self.in_place, self.engine = min_event_obs, in_place, engine
         self._reading = None   # (pending, iterator over read results)
         self._writing = []     # [(reads being written, iterator over write results, file names)]
+        self._n_batches = 0
 
-    # ---- stage 1: FAST5 reads of a batch, on the I/O processes
+    def _native(self, pending):
+        """file work of this batch through libnrqio (nrq_io.h: nrqio_f5_*) rather than hdf5_min.py on the I/O
+        processes: files on disk, write-back wanted, and a normalisation that needs no basecall events"""
+        return (self.in_place and self.norm_type in ('median', 'none', 'pA_raw')
+                and os.environ.get('NRQ_FAST5_NATIVE', '1') != '0'
+                and not any(str(pr.fast5_fn).startswith('mem://') for pr in pending))
+
+    # ---- stage 1: FAST5 reads of a batch, on the I/O processes (or libnrqio's threads)
     def _start_reads(self, pending):
         from . import fast5_jobs
+        if self._native(pending):
+            self._n_batches += 1
+            return pending, _Later(_io_thread().submit(self._load_native, pending, _batcher(self._n_batches & 1)))
         jobs = [(pr.fast5_fn, self.norm_type, self.basecall_group, pr.read_info.Subgroup) for pr in pending]
         return pending, fast5_jobs.start_jobs(fast5_jobs.read_job, jobs)
+
+    def _load_native(self, pending, batcher):
+        """resquiggle.py:327-347 for a whole batch: libnrqio opens the files, finds the signals and inflates them
+        straight into the pinned raw array of `batcher`; the other CSR arrays are filled from the alignment data.
+        A file outside libnrqio's HDF5 slice is read by hdf5_min.py instead; a read that cannot be loaded fails with
+        the message the reference gives."""
+        from . import _libio, fast5_jobs
+        n = len(pending)
+        fb = _libio.F5RawBatch([pr.fast5_fn for pr in pending])
+        try:
+            lens = fb.n_samples.copy()
+            channel = fb.channel.copy()
+            slow, failed = {}, []
+
+            def python_read(i):
+                got = fast5_jobs.read_job((pending[i].fast5_fn, self.norm_type, self.basecall_group,
+                                           pending[i].read_info.Subgroup))
+                if got[0] != 'ok':
+                    return got[1]
+                chan, raw = got[1], np.ascontiguousarray(got[2], dtype=np.int16)
+                slow[i] = raw
+                lens[i] = len(raw)
+                channel[i] = (chan.offset, chan.range, chan.digitisation, chan.sampling_rate)
+                return None
+
+            keep = np.ones(n, dtype=bool)
+            for i in np.nonzero(fb.status != _libio.F5_OK)[0]:
+                err = python_read(int(i))
+                if err is not None:
+                    failed.append((err, pending[i]))
+                    keep[i] = False
+            for i, pr in enumerate(pending):  # what PinnedBatcher.add refuses, per read
+                if keep[i] and (len(pr.rows[0]) != len(pr.rows[1]) or
+                                (len(pr.starts) and int(pr.starts[-1]) > np.iinfo(np.int32).max)):
+                    failed.append(('alignment rows differ in length' if len(pr.rows[0]) != len(pr.rows[1])
+                                   else 'read longer than 2^31 samples', pr))
+                    keep[i] = False
+            idx = np.nonzero(keep)[0]
+            ready = [pending[i] for i in idx]
+            given = None
+            if self.norm_type != 'median':
+                given = [nh.given_shift_scale(self.norm_type, nh.channelInfo(
+                    channel[i][0], channel[i][1], channel[i][2], None, int(channel[i][3]))) for i in idx]
+            raw_off = batcher.fill(
+                lens[idx], [int(pr.read_start) for pr in ready], [pr.starts for pr in ready],
+                [pr.rows[0].encode() for pr in ready], [pr.rows[1].encode() for pr in ready], given)
+            dst_off = np.full(n, -1, dtype=np.int64)
+            dst_off[idx] = raw_off[:-1]
+            for i in slow:
+                dst_off[i] = -1
+            status = fb.read_into(batcher.raw, dst_off)
+        finally:
+            fb.close()
+        unreadable = {}
+        for k, i in enumerate(idx):
+            lo, hi = int(raw_off[k]), int(raw_off[k + 1])
+            if i not in slow and status[i] != _libio.F5_OK:  # e.g. a filter libnrqio does not undo: hdf5_min's turn
+                err = python_read(int(i))
+                if err is None and len(slow[i]) != hi - lo:
+                    err = msg.OPEN_FOR_RESQUIGGLE
+                if err is not None:
+                    slow.pop(i, None)
+                    batcher.raw[lo:hi] = 0
+                    unreadable[k] = err
+            if i in slow:
+                batcher.raw[lo:hi] = slow[i]
+        if self.norm_type != 'median':
+            for pr, g in zip(ready, given):
+                pr.given = g
+        return [_LoadedBatch(ready, failed, unreadable, batcher)]
 
     # ---- stage 2: one device batch (a1..a7), then the write-backs are queued
     def _process(self, pending, loaded):
         from . import fast5_jobs
         from .engine import ResquiggleParams, get_engine
+        if loaded and isinstance(loaded[0], _LoadedBatch):
+            return self._process_native(loaded[0])
         norm_type = self.norm_type
         failed, ready = [], []
         for pr, got in zip(pending, loaded):
@@ -320,6 +434,99 @@ class BatchPipeline(object):
             self._writing.append((writers, fast5_jobs.start_jobs(fast5_jobs.write_packed_job, writes),
                                   set(pr.fast5_fn for pr in writers)))
         return failed
+
+    def _process_native(self, lb):
+        """the device batch of a _LoadedBatch, then its write-backs: libnrqio packs the gzip chunks from the pinned
+        result arrays and appends the RawGenomeCorrected groups to the files (nrqio_f5_write_corrected_batch) on
+        the background thread, while the next batch goes through the device"""
+        from . import _libio
+        from .engine import ResquiggleParams, get_engine
+        failed, ready, batcher = list(lb.failed), lb.ready, lb.batcher
+        if not ready:
+            return failed
+        norm_type = self.norm_type
+        engine = self.engine or get_engine()
+        params = ResquiggleParams(
+            norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=self.outlier_thresh,
+            compute_sd=self.compute_sd, num_cpts_limit=self.num_cpts_limit, timeout=self.timeout,
+            min_event_obs=self.min_event_obs)
+        res = engine.run_host(batcher, params, skip=('new_segs', 'ev_start', 'region_samples', 'n_indels'))
+        chunks, off, ln = _libio.pack_corrected(res.c_batch, res.c_results, len(ready))
+        sel = []
+        for r, pr in enumerate(ready):
+            if r in lb.unreadable:
+                failed.append((lb.unreadable[r], pr))
+                continue
+            exc = exception_for(res.status[r])
+            if exc is not None:
+                failed.append((str(exc), pr))
+                continue
+            sel.append(r)
+        if not sel:
+            return failed
+        sel = np.asarray(sel, dtype=np.int64)
+        writers = [ready[r] for r in sel]
+        sv = np.array(res.scale_values, dtype=np.float64).reshape(-1, 4)[sel]
+        if norm_type != 'median':
+            sv[:, :2] = np.asarray([pr.given for pr in writers], dtype=np.float64)
+        # attributes go out as int64 / float64 / str from libnrqio; anything else (numpy ints of another width, a
+        # missing clip limit, ...) is typed by the Python writer's h5py rules, as the reference's would be
+        def plain_int(v):
+            return type(v) is int or isinstance(v, np.int64)
+
+        ints = np.zeros((len(writers), 8), dtype=np.int64)
+        odd = np.zeros(len(writers), dtype=np.int32)
+        for k, pr in enumerate(writers):
+            vals = (pr.genome_loc.Start, pr.read_info.ClipStart, pr.read_info.ClipEnd, pr.read_info.Insertions,
+                    pr.read_info.Deletions, pr.read_info.Matches, pr.read_info.Mismatches, pr.read_start)
+            try:
+                if not all(plain_int(v) for v in vals) or np.isnan(sv[k]).any() or \
+                        not isinstance(pr.genome_loc.Strand, str) or not isinstance(pr.genome_loc.Chrom, str) or \
+                        pr.read_info.Subgroup != writers[0].read_info.Subgroup:
+                    odd[k] = 1
+                else:
+                    ints[k] = vals
+            except (TypeError, ValueError, OverflowError):
+                odd[k] = 1
+        if norm_type == 'none' or type(self.outlier_thresh) not in (int, float):
+            odd[:] = 1
+        job = dict(
+            writers=writers, sv=sv, ints=ints, odd=odd, n_bases=np.array(res.n_bases, dtype=np.int32)[sel],
+            n_align=np.diff(np.asarray(res.align_off))[sel], n_segs=np.diff(np.asarray(batcher.starts_off[:len(ready) + 1]))[sel],
+            chunks=chunks, off=off.reshape(-1, 4)[sel].copy(), ln=ln.reshape(-1, 4)[sel].copy())
+        self._writing.append((writers, _Later(_io_thread().submit(self._write_native, job)),
+                              set(pr.fast5_fn for pr in writers)))
+        return failed
+
+    def _write_native(self, job):
+        """-> [None | error message] per writer (resquiggle.py:80-135 and its error strings)"""
+        from . import _libio, fast5_jobs
+        writers, sv, chunks, off, ln = job['writers'], job['sv'], job['chunks'], job['off'], job['ln']
+        odd = job['odd']
+        if not odd.all():
+            status = _libio.f5_write_corrected(
+                [pr.fast5_fn for pr in writers], self.corrected_group, writers[0].read_info.Subgroup, self.norm_type,
+                self.outlier_thresh, [str(pr.genome_loc.Chrom) for pr in writers],
+                [str(pr.genome_loc.Strand) for pr in writers], sv, job['ints'], job['n_bases'], job['n_align'],
+                job['n_segs'], chunks, off, ln, skip=odd)
+        else:
+            status = np.zeros(len(writers), dtype=np.int32)
+        errs = []
+        for k, pr in enumerate(writers):
+            st = int(status[k])
+            if st == _libio.F5_OK and not odd[k]:
+                errs.append(None)
+            elif st == _libio.F5_EXISTS:
+                errs.append(msg.WRITE_BACK)
+            elif st == _libio.F5_IO:
+                errs.append(msg.OPEN_FOR_WRITE)
+            else:  # outside libnrqio's HDF5 slice (or another subgroup name): hdf5_min.py rewrites the file
+                packed = (int(job['n_bases'][k]), int(job['n_align'][k]), int(job['n_segs'][k])) + tuple(
+                    chunks[off[k, j]:off[k, j] + ln[k, j]].tobytes() for j in range(4))
+                errs.append(fast5_jobs.write_packed_job((
+                    pr.fast5_fn, pr.genome_loc, pr.read_info, pr.read_start, packed, nh.scaleValues(*sv[k]),
+                    self.corrected_group, pr.read_info.Subgroup, self.norm_type, self.outlier_thresh)))
+        return errs
 
     # ---- stage 3: results of the write-backs
     def _collect_writes(self, keep=0):
