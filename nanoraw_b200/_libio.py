@@ -16,6 +16,7 @@ SYMBOLS = {
     'nrqio_deflate_bound': (C.c_int64, [C.c_int64]),
     'nrqio_deflate': (C.c_int64, [_P, C.c_int64, _P, C.c_int64]),
     'nrqio_adler32': (C.c_uint32, [_P, C.c_int64]),
+    'nrqio_inflate': (C.c_int64, [_P, C.c_int64, _P, C.c_int64]),
     'nrqio_pack_corrected_bound': (C.c_int64, [C.POINTER(_lib.NrqBatch), C.POINTER(_lib.NrqResults), C.c_int32,
                                                C.c_int32]),
     'nrqio_pack_corrected': (C.c_int, [C.POINTER(_lib.NrqBatch), C.POINTER(_lib.NrqResults), C.c_int32, C.c_int32,
@@ -93,6 +94,15 @@ def deflate(data):
     if n < 0:
         raise _lib.NrqError('nrqio_deflate failed')
     return dst[:n].tobytes()
+
+
+def inflate(data, size):
+    """bytes of the zlib stream `data`, which must hold at most `size` of them (nrqio_inflate); None if refused"""
+    lib = load()
+    src = np.frombuffer(data, dtype=np.uint8) if len(data) else np.zeros(1, np.uint8)
+    dst = np.empty(max(int(size), 1), dtype=np.uint8)
+    n = int(lib.nrqio_inflate(src.ctypes.data, len(data), dst.ctypes.data, int(size)))
+    return None if n < 0 else dst[:n].tobytes()
 
 
 def pack_threads():

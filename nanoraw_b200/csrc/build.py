@@ -24,7 +24,7 @@ def _stale():
 
 
 IO_LIB = os.path.join(PKG, 'libnrqio.so')
-IO_SOURCES = ['nrq_io.cpp', 'nrq_fast5.cpp', os.path.join('..', '..', 'include', 'nrq_io.h'), os.path.join('..', '..', 'include', 'nrq.h')]
+IO_SOURCES = ['nrq_io.cpp', 'nrq_fast5.cpp', 'nrq_inflate.cpp', os.path.join('..', '..', 'include', 'nrq_io.h'), os.path.join('..', '..', 'include', 'nrq.h')]
 
 
 def build_io(force=False, verbose=False):
@@ -33,7 +33,8 @@ def build_io(force=False, verbose=False):
             os.path.getmtime(os.path.join(HERE, s)) <= os.path.getmtime(IO_LIB) for s in IO_SOURCES):
         return IO_LIB
     cmd = [os.environ.get('CXX', 'g++'), '-O3', '-std=c++17', '-shared', '-fPIC', '-pthread', '-o', IO_LIB,
-           os.path.join(HERE, 'nrq_io.cpp'), os.path.join(HERE, 'nrq_fast5.cpp'), '-lz']
+           os.path.join(HERE, 'nrq_io.cpp'), os.path.join(HERE, 'nrq_fast5.cpp'),
+           os.path.join(HERE, 'nrq_inflate.cpp'), '-lz']
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -501,6 +501,8 @@ void list_chunks(const File& f, uint64_t node, std::vector<Chunk>& out, int dept
 }
 
 void inflate_into(const uint8_t* src, uint64_t n_src, uint8_t* dst, uint64_t n_dst) {
+  if (nrqio_inflate(src, (int64_t)n_src, dst, (int64_t)n_dst) == (int64_t)n_dst) return;
+  // refused by the fast decoder: zlib has the last word on whether the stream is valid
   uLongf got = (uLongf)n_dst;
   const int rc = uncompress(dst, &got, src, (uLong)n_src);
   F5_REQUIRE(rc == Z_OK && (uint64_t)got == n_dst, NRQIO_F5_FORMAT);

@@ -202,3 +202,62 @@ def test_h5py_reads_what_the_native_writer_and_the_packer_produce(tmp_path, monk
         assert grp['Alignment/read_alignment'][()].tobytes() == read.read_align
         assert np.array_equal(grp['Alignment/read_segments'][()], read.starts)
         assert grp.attrs['shift'] == 1.0 and grp['Alignment'].attrs['mapped_chrom'] in ('c', b'c')
+
+
+# ----------------------------------------------------------------------------------------------- nrqio_inflate
+def _zlib_streams(data):
+    """the same bytes as every kind of deflate stream zlib can write, plus this library's own encoder"""
+    for level in (0, 1, 4, 6, 9):
+        yield zlib.compress(data, level)
+    for strategy in (zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+        c = zlib.compressobj(6, zlib.DEFLATED, 15, 8, strategy)
+        yield c.compress(data) + c.flush()
+    c = zlib.compressobj(6, zlib.DEFLATED, 9, 1)      # 512-byte window, smallest hash
+    yield c.compress(data) + c.flush()
+    c, out = zlib.compressobj(5), b''
+    for k in range(0, len(data), 1000):               # many blocks, with empty stored blocks between them
+        out += c.compress(data[k:k + 1000]) + c.flush(zlib.Z_SYNC_FLUSH if (k // 1000) % 2 else zlib.Z_FULL_FLUSH)
+    yield out + c.flush()
+    yield _libio.deflate(data)
+
+
+def test_inflate_equals_zlib_on_every_kind_of_stream():
+    rng = np.random.default_rng(0)
+    cases = [b'', b'a', b'abc' * 1000, bytes(range(256)) * 50, b'\x00' * 70000,
+             rng.integers(0, 256, 100000, dtype=np.uint8).tobytes(),
+             np.cumsum(rng.integers(-30, 31, 90000)).astype('<i2').tobytes(), (b'ACGT' * 3 + b'TTAG') * 5000,
+             rng.integers(0, 4, 50000, dtype=np.uint8).tobytes()]
+    cases += [r.raw.tobytes() for r in synth.make_reads(2, synth.config_short())]
+    for _ in range(40):
+        n, k = int(rng.integers(0, 3000)), int(rng.integers(1, 257))
+        cases.append(rng.choice(k, n, p=rng.dirichlet(np.ones(k) * 0.3)).astype(np.uint8).tobytes())
+    for data in cases:
+        for z in _zlib_streams(data):
+            assert zlib.decompress(z) == data
+            assert _libio.inflate(z, len(data)) == data
+            assert _libio.inflate(z, len(data) + 300) == data
+            if data:
+                assert _libio.inflate(z, len(data) - 1) is None      # more bytes than the caller has room for
+            for cut in (1, 2, 5, len(z) // 2, len(z) - 5, len(z) - 1):
+                if 0 < cut < len(z):
+                    assert _libio.inflate(z[:cut], len(data) + 10) is None
+            if len(z) > 12:                                           # one flipped bit: refused (or, with a stored
+                zz = bytearray(z)                                     # block's padding bits, harmless)
+                zz[int(rng.integers(2, len(z) - 4))] ^= 1 << int(rng.integers(0, 8))
+                assert _libio.inflate(bytes(zz), len(data) + 10) in (None, data)
+
+
+def test_inflate_refuses_garbage_without_touching_memory_outside():
+    rng = np.random.default_rng(1)
+    lib = _libio.load()
+    for k in range(3000):
+        n = int(rng.integers(0, 400))
+        junk = rng.integers(0, 256, n, dtype=np.uint8)
+        if n >= 2 and k % 2:
+            junk[0], junk[1] = 0x78, 0x9c                             # a valid zlib header in front of the noise
+        cap = int(rng.integers(0, 600))
+        dst = np.full(cap + 64, 0xAB, dtype=np.uint8)
+        src = np.concatenate([junk, np.zeros(1, np.uint8)])           # (so that an empty input has an address)
+        got = int(lib.nrqio_inflate(src.ctypes.data, n, dst[32:].ctypes.data, cap))
+        assert got == -1 or 0 <= got <= cap
+        assert (dst[:32] == 0xAB).all() and (dst[32 + cap:] == 0xAB).all()
