@@ -186,9 +186,10 @@ __device__ __forceinline__ int unpack16(const int4& q, int j) {
   return (int)(short)((j & 1) ? (w >> 16) : (w & 0xffff));
 }
 
-// 1/y for y >= 1 well inside float range: float seed + two Newton steps (a few ulps)
+// 1/y for y >= 1: the hardware's 20-bit double reciprocal + two Newton steps (a few ulps)
 __device__ __forceinline__ double ev_rcp(double y) {
-  double r = (double)__frcp_rn((float)y);
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y));
   r = fma(r, fma(-y, r, 1.0), r);
   r = fma(r, fma(-y, r, 1.0), r);
   return r;
@@ -209,9 +210,21 @@ __device__ __forceinline__ double ev_sqrt(double y) {
 }
 
 
+// sqrt of an integer-valued y in [0, 2^64): the seed is the hardware's 20-bit double rsqrt of y + 2^-60, which is y
+// itself for y >= 1 and keeps y = 0 finite, so that 0 comes out as 0 without a branch
+__device__ __forceinline__ double ev_sqrt_int(double y) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y + 0x1p-60));
+  const double h = 0.5 * y;
+  r = r * fma(-h * r, r, 1.5);
+  r = r * fma(-h * r, r, 1.5);
+  const double s = y * r;
+  return fma(fma(-s, s, y), 0.5 * r, s);
+}
+
 struct EvRead {       // per-read constants of the statistics
   double c_off;       // pivot - shift
-  double inv_scale, inv_scale2;
+  double inv_scale, inv_scale2, inv_scale_abs;
   double below_val, above_val;
   const double* rcp_tab;  // 1/n for n < 64
   int compute_sd;
@@ -386,6 +399,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   R.c_off = __dsub_rn((double)pivot, coef.shift);
   R.inv_scale = 1.0 / coef.scale;
   R.inv_scale2 = R.inv_scale * R.inv_scale;
+  R.inv_scale_abs = fabs(R.inv_scale);
   R.below_val = k.below_val;
   R.above_val = k.above_val;
   R.rcp_tab = rcp_tab;
@@ -541,13 +555,13 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             if (n > 0) {
               if ((nl | nh) == 0) {
                 const double dn = (double)n;
-                const double rn = (unsigned)n < 64u ? rcp_tab[n] : ev_rcp(dn);
+                const double rn = ev_rcp(dn);
                 const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
                 mean = sum_u * rn;
                 if (R.compute_sd) {
                   const unsigned long long num = (unsigned long long)(unsigned)n * (unsigned long long)S2 -
                                                  (unsigned long long)((long long)S1 * (long long)S1);
-                  sd = ev_sqrt((double)num * rn * R.inv_scale2 * rn);
+                  sd = ev_sqrt_int((double)num) * (rn * R.inv_scale_abs);  // sqrt(num / n^2 / scale^2)
                 }
               } else {
                 ev_base_stats(R, n, (long long)S1, (unsigned long long)S2, nl, nh, mean, sd);
@@ -578,13 +592,13 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const int S1 = E1 - pE1;        // |S1| <= S2 < 2^32: d is an integer
             const unsigned S2 = E2 - pE2;
             const double dn = (double)n;
-            const double rn = (unsigned)n < 64u ? rcp_tab[n] : ev_rcp(dn);
+            const double rn = ev_rcp(dn);
             const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
             double mean = sum_u * rn, sd = qnan;
             if (R.compute_sd) {
               const unsigned long long num =
                   (unsigned long long)(unsigned)n * (unsigned long long)S2 - (unsigned long long)((long long)S1 * (long long)S1);
-              sd = ev_sqrt((double)num * rn * R.inv_scale2 * rn);
+              sd = ev_sqrt_int((double)num) * (rn * R.inv_scale_abs);  // sqrt(num / n^2 / scale^2)
             }
             if (n <= 0) { mean = qnan; sd = qnan; }
             const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
