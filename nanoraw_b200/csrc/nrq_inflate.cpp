@@ -7,8 +7,6 @@
 // second-level tables behind them, and word-wise match copies.  It never reads outside [src, src + n) nor writes
 // outside [dst, dst + cap): close to either end it switches to a byte-wise loop.  The Adler-32 of the output is
 // checked like zlib's uncompress does.  Part of libnrqio.so.
-#include <zlib.h>
-
 #include <cstdint>
 #include <cstring>
 
@@ -368,12 +366,7 @@ extern "C" int64_t nrqio_inflate(const uint8_t* src, int64_t n, uint8_t* dst, in
   const uint8_t* tail = src + 2 + used;
   if (src + n - tail < 4) return -1;
   const uint32_t want = ((uint32_t)tail[0] << 24) | ((uint32_t)tail[1] << 16) | ((uint32_t)tail[2] << 8) | tail[3];
-  uLong a = adler32(0L, Z_NULL, 0);
-  for (int64_t done = 0; done < got;) {  // (uInt lengths)
-    const int64_t step = got - done > (1 << 30) ? (1 << 30) : got - done;
-    a = adler32(a, dst + done, (uInt)step);
-    done += step;
-  }
-  if ((uint32_t)a != want) return -1;
+  const uint32_t a = nrqio_adler32(dst, got);
+  if (a != want) return -1;
   return got;
 }

@@ -261,3 +261,19 @@ def test_inflate_refuses_garbage_without_touching_memory_outside():
         got = int(lib.nrqio_inflate(src.ctypes.data, n, dst[32:].ctypes.data, cap))
         assert got == -1 or 0 <= got <= cap
         assert (dst[:32] == 0xAB).all() and (dst[32 + cap:] == 0xAB).all()
+
+
+def test_adler32_equals_zlib():
+    """the vector path (32 bytes per step, runs of 173 steps) against zlib: lengths around every boundary of the
+    algorithm, the contents that overflow first, unaligned starts"""
+    lib = _libio.load()
+    rng = np.random.default_rng(2)
+    for n in [0, 1, 2, 31, 32, 33, 63, 64, 65, 100, 5535, 5536, 5537, 5552, 5553, 11072, 11073, 100000, 242000, (1 << 21) + 7]:
+        for kind in range(3):
+            data = rng.integers(0, 256, n, dtype=np.uint8) if kind == 0 else np.full(n, 255 if kind == 1 else 0, np.uint8)
+            buf = np.concatenate([data, np.zeros(1, np.uint8)])
+            assert lib.nrqio_adler32(buf.ctypes.data, n) == zlib.adler32(data.tobytes()), (n, kind)
+    for _ in range(200):
+        n, off = int(rng.integers(0, 20000)), int(rng.integers(0, 40))
+        base = rng.integers(0, 256, n + off + 1, dtype=np.uint8)
+        assert lib.nrqio_adler32(base[off:].ctypes.data, n) == zlib.adler32(base[off:off + n].tobytes())
