@@ -566,10 +566,40 @@ def _libio_threads():
     return _libio.f5_threads()
 
 
+def host_work_per_read(jobs, pend, reads_per_s):
+    """What bounds the FAST5 leg: the host work per read of each stage of the worker, measured by running a sample
+    of the leg's own files through the same pipeline on ONE thread (NRQ_F5_THREADS = NRQ_PACK_THREADS = 1), and
+    the reads/s the host cores of this rank could do at that cost -- the leg's equivalent of a roofline."""
+    from nanoraw_b200 import fast5_jobs
+    from nanoraw_b200 import resquiggle as rsq
+    fast5_jobs.map_jobs(synth.drop_corrected_job, jobs)          # back to the state prep_fast5 leaves
+    saved = {k: os.environ.get(k) for k in ('NRQ_F5_THREADS', 'NRQ_PACK_THREADS')}
+    os.environ['NRQ_F5_THREADS'] = os.environ['NRQ_PACK_THREADS'] = '1'
+    try:
+        pipe = rsq.BatchPipeline('median', 5, None, None, 'Basecall_1D_000', 'RawGenomeCorrected_000', True, None)
+        failed = pipe.feed(pend) + pipe.drain()
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    n = max(len(pend) - len(failed), 1)
+    ms = {k: round(1e3 * v / n, 4) for k, v in pipe.stage_seconds.items()}
+    cores = max(1, host_cores() // max(1, int(os.environ.get('WORLD_SIZE', '1'))))
+    cpu_ms = sum(v for k, v in ms.items() if k != 'device')
+    bound = 1e3 * cores / cpu_ms if cpu_ms > 0 else None
+    return {'ms_per_read_one_thread': ms, 'sample_reads': n, 'cores_of_this_rank': cores,
+            'bound_reads_per_s': bound, 'frac_of_bound': (reads_per_s / bound) if bound else None,
+            'what': 'open = file read + HDF5 walk, fill = CSR arrays of the batch (Python), inflate = raw signal into '
+                    'pinned staging, device = nrq_resquiggle_batch_host, pack = four gzip chunks per read, append = '
+                    'RawGenomeCorrected group written into the file; bound = cores / (sum without device)'}
+
+
 def fast5_leg(args, reads, barrier=None):
     """The re-squiggle worker's whole body (resquiggle.py:403-440 -> 318-401) on FAST5 files on disk: open each
     file and read its raw signal, one device batch through the C ABI, RawGenomeCorrected written back into each
-    file.  File access is this repo's own HDF5 reader / writer on NRQ_IO_PROCS host processes.  Alignments are
+    file.  File access is libnrqio's FAST5 functions (include/nrq_io.h) on NRQ_F5_THREADS host threads.  Alignments are
     the synthetic ones (the mapper stays external), handed over as the queue items the alignment workers make."""
     import shutil
     import tempfile
@@ -610,6 +640,7 @@ def fast5_leg(args, reads, barrier=None):
         dt = time.perf_counter() - t0
         samples_of = {fn: read.n_samples for fn, read in jobs}
         ok_samples = sum(samples_of.values()) - sum(samples_of[pr.fast5_fn] for _, pr in failed)
+        host = host_work_per_read(jobs[:min(n, 128)], pending_reads()[:min(n, 128)], (n - len(failed)) / dt)
         # spot check of what landed on disk
         f = fast5_io.open_fast5(jobs[0][0], 'r')
         ev = f['/Analyses/RawGenomeCorrected_000/BaseCalled_template/Events'][()]
@@ -619,7 +650,7 @@ def fast5_leg(args, reads, barrier=None):
                 'failed_reads': len(failed), 'seconds': dt, 'io_procs': fast5_jobs.io_procs(),
                 'bytes_per_file_in': int(np.mean(sizes)), 'events_rows_file0': int(len(ev)),
                 'setup_seconds': setup_s,
-                'f5_threads': _libio_threads(),
+                'f5_threads': _libio_threads(), 'host_work': host,
                 'what': 'resquiggle.BatchPipeline (the re-squiggle worker body): FAST5 open + raw signal inflated '
                         'into pinned staging (libnrqio threads), device batch, datasets packed into gzip chunks and '
                         'the RawGenomeCorrected group appended to the same file (libnrqio threads; hdf5_min.py '

@@ -17,6 +17,7 @@ reproduced.
 import os
 import queue
 import sys
+import time
 from collections import namedtuple
 
 import numpy as np
@@ -261,7 +262,14 @@ class _PendingRead(object):
         self.fast5_fn = fast5_fn
         self.raw = None
         self.given = None
-        self.rows = _rows(self.alignVals)
+        # the two alignment rows as bytes, which is what the device batch takes (the reference's list of pairs and
+        # str rows are converted once, here)
+        av = self.alignVals
+        if isinstance(av, tuple) and len(av) == 2 and isinstance(av[0], bytes) and isinstance(av[1], bytes):
+            self.rows = av
+        else:
+            ra, ga = _rows(av)
+            self.rows = (ra.encode(), ga.encode())
 
 
 class BatchPipeline(object):
@@ -282,6 +290,9 @@ class BatchPipeline(object):
         self._reading = None   # (pending, iterator over read results)
         self._writing = []     # [(reads being written, iterator over write results, file names)]
         self._n_batches = 0
+        # wall seconds spent in each stage of the native file path (libnrqio), summed over batches: with
+        # NRQ_F5_THREADS=1 and NRQ_PACK_THREADS=1 these are the single-core costs per read that bound the worker
+        self.stage_seconds = {'open': 0.0, 'fill': 0.0, 'inflate': 0.0, 'device': 0.0, 'pack': 0.0, 'append': 0.0}
 
     def _native(self, pending):
         """file work of this batch through libnrqio (nrq_io.h: nrqio_f5_*) rather than hdf5_min.py on the I/O
@@ -306,7 +317,9 @@ class BatchPipeline(object):
         the message the reference gives."""
         from . import _libio, fast5_jobs
         n = len(pending)
+        t_0 = time.perf_counter()
         fb = _libio.F5RawBatch([pr.fast5_fn for pr in pending])
+        self.stage_seconds['open'] += time.perf_counter() - t_0
         try:
             lens = fb.n_samples.copy()
             channel = fb.channel.copy()
@@ -341,14 +354,18 @@ class BatchPipeline(object):
             if self.norm_type != 'median':
                 given = [nh.given_shift_scale(self.norm_type, nh.channelInfo(
                     channel[i][0], channel[i][1], channel[i][2], None, int(channel[i][3]))) for i in idx]
+            t_0 = time.perf_counter()
             raw_off = batcher.fill(
                 lens[idx], [int(pr.read_start) for pr in ready], [pr.starts for pr in ready],
-                [pr.rows[0].encode() for pr in ready], [pr.rows[1].encode() for pr in ready], given)
+                [pr.rows[0] for pr in ready], [pr.rows[1] for pr in ready], given)
             dst_off = np.full(n, -1, dtype=np.int64)
             dst_off[idx] = raw_off[:-1]
             for i in slow:
                 dst_off[i] = -1
+            t_1 = time.perf_counter()
             status = fb.read_into(batcher.raw, dst_off)
+            self.stage_seconds['fill'] += t_1 - t_0
+            self.stage_seconds['inflate'] += time.perf_counter() - t_1
         finally:
             fb.close()
         unreadable = {}
@@ -393,7 +410,7 @@ class BatchPipeline(object):
         batcher = _batcher()
         batcher.reset()
         for pr in ready:  # straight into pinned CSR staging: no intermediate copies
-            batcher.add(pr.raw, int(pr.read_start), pr.starts, pr.rows[0].encode(), pr.rows[1].encode(),
+            batcher.add(pr.raw, int(pr.read_start), pr.starts, pr.rows[0], pr.rows[1],
                         None if norm_type == 'median' else (float(pr.given[0]), float(pr.given[1])))
         params = ResquiggleParams(
             norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=self.outlier_thresh,
@@ -450,21 +467,22 @@ class BatchPipeline(object):
             norm_type='median' if norm_type == 'median' else 'given', outlier_thresh=self.outlier_thresh,
             compute_sd=self.compute_sd, num_cpts_limit=self.num_cpts_limit, timeout=self.timeout,
             min_event_obs=self.min_event_obs)
+        t_0 = time.perf_counter()
         res = engine.run_host(batcher, params, skip=('new_segs', 'ev_start', 'region_samples', 'n_indels'))
+        t_1 = time.perf_counter()
         chunks, off, ln = _libio.pack_corrected(res.c_batch, res.c_results, len(ready))
-        sel = []
-        for r, pr in enumerate(ready):
-            if r in lb.unreadable:
-                failed.append((lb.unreadable[r], pr))
-                continue
-            exc = exception_for(res.status[r])
-            if exc is not None:
-                failed.append((str(exc), pr))
-                continue
-            sel.append(r)
-        if not sel:
+        self.stage_seconds['device'] += t_1 - t_0
+        self.stage_seconds['pack'] += time.perf_counter() - t_1
+        good = np.asarray(res.status[:len(ready)]) == 0
+        for r in lb.unreadable:
+            good[r] = False
+            failed.append((lb.unreadable[r], ready[r]))
+        for r in np.flatnonzero(np.asarray(res.status[:len(ready)]) != 0):
+            if int(r) not in lb.unreadable:
+                failed.append((str(exception_for(res.status[r])), ready[r]))
+        sel = np.flatnonzero(good)
+        if not len(sel):
             return failed
-        sel = np.asarray(sel, dtype=np.int64)
         writers = [ready[r] for r in sel]
         sv = np.array(res.scale_values, dtype=np.float64).reshape(-1, 4)[sel]
         if norm_type != 'median':
@@ -476,13 +494,15 @@ class BatchPipeline(object):
 
         ints = np.zeros((len(writers), 8), dtype=np.int64)
         odd = np.zeros(len(writers), dtype=np.int32)
+        no_limits = np.isnan(sv).any(axis=1)
+        subgroup = writers[0].read_info.Subgroup
         for k, pr in enumerate(writers):
             vals = (pr.genome_loc.Start, pr.read_info.ClipStart, pr.read_info.ClipEnd, pr.read_info.Insertions,
                     pr.read_info.Deletions, pr.read_info.Matches, pr.read_info.Mismatches, pr.read_start)
             try:
-                if not all(plain_int(v) for v in vals) or np.isnan(sv[k]).any() or \
+                if not all(plain_int(v) for v in vals) or no_limits[k] or \
                         not isinstance(pr.genome_loc.Strand, str) or not isinstance(pr.genome_loc.Chrom, str) or \
-                        pr.read_info.Subgroup != writers[0].read_info.Subgroup:
+                        pr.read_info.Subgroup != subgroup:
                     odd[k] = 1
                 else:
                     ints[k] = vals
@@ -503,6 +523,7 @@ class BatchPipeline(object):
         from . import _libio, fast5_jobs
         writers, sv, chunks, off, ln = job['writers'], job['sv'], job['chunks'], job['off'], job['ln']
         odd = job['odd']
+        t_0 = time.perf_counter()
         if not odd.all():
             status = _libio.f5_write_corrected(
                 [pr.fast5_fn for pr in writers], self.corrected_group, writers[0].read_info.Subgroup, self.norm_type,
@@ -511,6 +532,7 @@ class BatchPipeline(object):
                 job['n_segs'], chunks, off, ln, skip=odd)
         else:
             status = np.zeros(len(writers), dtype=np.int32)
+        self.stage_seconds['append'] += time.perf_counter() - t_0
         errs = []
         for k, pr in enumerate(writers):
             st = int(status[k])

@@ -126,3 +126,90 @@ def test_alignment_worker_to_resquiggle_worker(tmp_path, monkeypatch, backend):
     assert len(skipped) == len(names)
     assert all(e == 'Raw genome corrected data exists for this read and --overwrite is not set.'
                for e, _ in skipped)
+
+
+def test_native_file_path_equals_the_python_one(tmp_path, monkeypatch):
+    """BatchPipeline on files on disk, once with libnrqio's FAST5 functions and once with hdf5_min.py on the I/O
+    processes (NRQ_FAST5_NATIVE=0): the same failures with the same messages, and object trees that are equal
+    file by file -- including the files the native path hands to the Python reader / writer."""
+    import shutil
+    from nanoraw_b200 import hdf5_min, messages as msg
+    from nanoraw_b200 import resquiggle as rsq
+    from nanoraw_b200.frontend import genomeLoc, readInfo
+    monkeypatch.setattr(fast5_io, '_BACKEND', ['native'])
+    monkeypatch.setenv('NRQ_IO_PROCS', '0')
+    reads = synth.make_reads(9, synth.config_short())
+    dirs = {}
+    for mode in ('native', 'python'):
+        d = tmp_path / mode
+        d.mkdir()
+        dirs[mode] = d
+    base = []
+    for i, r in enumerate(reads):
+        fn = str(dirs['native'] / ('read_%d.fast5' % i))
+        synth.write_basecalled_fast5_job((fn, r))
+        base.append(fn)
+    # 2: float32 signal (libnrqio refuses the type, the Python reader converts); 3: not an HDF5 file;
+    # 4: already corrected (create_group raises); 5: no RawGenomeCorrected_000 group (prep_fast5 has not run)
+    f = fast5_io.open_fast5(base[2], 'r+')
+    del f['/Raw/Reads/Read_1/Signal']
+    f['/Raw/Reads/Read_1'].create_dataset('Signal', data=reads[2].raw.astype(np.float32), compression='gzip')
+    f.close()
+    open(base[3], 'wb').write(b'\x89HDF\r\n\x1a\n' + b'\x00' * 50)
+    f = fast5_io.open_fast5(base[4], 'r+')
+    f['/Analyses/RawGenomeCorrected_000'].create_group('BaseCalled_template')
+    f.close()
+    f = fast5_io.open_fast5(base[5], 'r+')
+    del f['/Analyses/RawGenomeCorrected_000']
+    f.close()
+    for fn in base:
+        shutil.copy(fn, str(dirs['python'] / os.path.basename(fn)))
+
+    def run(mode):
+        monkeypatch.setenv('NRQ_FAST5_NATIVE', '1' if mode == 'native' else '0')
+        pend = []
+        for i, r in enumerate(reads):
+            fn = str(dirs[mode] / ('read_%d.fast5' % i))
+            info = readInfo(os.path.basename(fn), 'BaseCalled_template', 1, 2, 3, 4, 5, 6)
+            # 6: a numpy int32 where an int is usual (typed by h5py's rules on the Python writer)
+            start = np.int32(r.genome_start) if i == 6 else int(r.genome_start)
+            loc = genomeLoc(start, r.strand, r.chrom)
+            pend.append(rsq._PendingRead(fn, ((r.read_align, r.genome_align), loc, r.starts,
+                                              int(r.read_start_rel_to_raw), info)))
+        pipe = rsq.BatchPipeline('median', 5, None, None, 'Basecall_1D_000', 'RawGenomeCorrected_000', True, None)
+        assert pipe._native(pend) == (mode == 'native')
+        failed = pipe.feed(pend[:5]) + pipe.feed(pend[5:]) + pipe.drain()
+        return sorted((os.path.basename(pr.fast5_fn), text) for text, pr in failed)
+
+    def tree(fn):
+        root, lossy = hdf5_min.load_tree(open(fn, 'rb').read())
+        out = {}
+
+        def visit(g, path):
+            out[path + '@'] = {k: (np.asarray(v).dtype.str, np.asarray(v).tolist()) for k, v in g.attrs.items()}
+            if isinstance(g, fast5_io.MemGroup):
+                for k, c in g._children.items():
+                    visit(c, path + '/' + k)
+            else:
+                a = g[()]
+                out[path] = (str(a.dtype), a.shape, a.tobytes(), g.compression)
+        visit(root, '')
+        return out
+
+    failed_native, failed_python = run('native'), run('python')
+    assert failed_native == failed_python
+    assert failed_native == [('read_3.fast5', msg.OPEN_FOR_RESQUIGGLE), ('read_4.fast5', msg.WRITE_BACK),
+                             ('read_5.fast5', msg.WRITE_BACK)]
+    for i in range(len(reads)):
+        if i == 3:
+            continue
+        a = tree(str(dirs['native'] / ('read_%d.fast5' % i)))
+        b = tree(str(dirs['python'] / ('read_%d.fast5' % i)))
+        assert a.keys() == b.keys(), i
+        for k in a:
+            assert a[k] == b[k], (i, k)
+        if i not in (4, 5):
+            assert '/Analyses/RawGenomeCorrected_000/BaseCalled_template/Events' in a
+    assert a['/Analyses/RawGenomeCorrected_000/BaseCalled_template/Alignment@']['mapped_start'][0] == '<i8'
+    six = tree(str(dirs['native'] / 'read_6.fast5'))
+    assert six['/Analyses/RawGenomeCorrected_000/BaseCalled_template/Alignment@']['mapped_start'][0] == '<i4'
