@@ -140,3 +140,60 @@ def test_pinned_batcher_packs_like_readbatch_and_grows():
     assert pb.has_given and pb.scale_values_in[0] == 1.5 and np.isnan(pb.scale_values_in[2])
     with pytest.raises(ValueError):
         pb.add(reads[0].raw, 0, reads[0].starts, b'AC', b'A')
+
+
+def test_worker_reports_a_device_failure_against_the_batch_it_hit(monkeypatch):
+    """ADVICE (round 1): when the device batch of the PREVIOUS feed raises, exactly that batch's reads are reported,
+    once each, and the batch whose file reads had just been started goes through afterwards (resquiggle.py:434-438
+    per read -> per batch here).  The engine is a stand-in: no device is needed for the bookkeeping."""
+    import queue
+    from nanoraw_b200 import fast5_io, resquiggle as rsq, synth
+    monkeypatch.setattr(rsq, 'DEVICE_BATCH_READS', 3)
+    monkeypatch.setattr(rsq, '_BATCHER', [])
+    cfg = synth.SynthConfig(span_mean=300, span_sd=30, seed_base=91000)
+    genome = synth.make_genome(20_000, seed=5)
+    names = []
+    basecalls_q, failed_q = queue.Queue(), queue.Queue()
+    for i in range(8):
+        read = synth.make_read(genome, synth.kmer_levels(cfg), cfg, i)
+        name = 'mem://failsafe/read_%d.fast5' % i
+        f = fast5_io.open_fast5(name, 'w')
+        rd = f.create_group('Raw/Reads/Read_1')
+        rd.create_dataset('Signal', data=read.raw)
+        ch = f.create_group('UniqueGlobalKey/channel_id')
+        for k, v in (('offset', 1.0), ('range', 1400.0), ('digitisation', 8192.0), ('sampling_rate', 4000.0)):
+            ch.attrs[k] = np.float64(v)
+        ch.attrs['channel_number'] = '1'
+        f.close()
+        names.append(name)
+        info = rsq.readInfo('r%d' % i, 'BaseCalled_template', 0, 0, 0, 0, 0, 0)
+        basecalls_q.put((name, [((read.read_align, read.genome_align), rsq.genomeLoc(0, '+', 'chr'), read.starts,
+                                 read.read_start_rel_to_raw, info)]))
+    basecalls_q.put((None, None))
+
+    class Result(object):
+        def __init__(self, n):
+            self.status = np.zeros(n, dtype=np.int32)
+
+    class Engine(object):
+        calls = 0
+
+        def run_host(self, batcher, params, skip=()):
+            Engine.calls += 1
+            if Engine.calls == 2:
+                raise RuntimeError('device fell over')
+            return Result(batcher.n_reads)
+
+    real = rsq.BatchPipeline
+
+    def pipeline(*a, **kw):
+        kw.update(in_place=False, engine=Engine())
+        return real(*a, **kw)
+
+    monkeypatch.setattr(rsq, 'BatchPipeline', pipeline)
+    rsq.resquiggle_worker(basecalls_q, failed_q, 'Basecall_1D_000', 'RawGenomeCorrected_000', 'median', 5,
+                          None, None, True, None)
+    failed = [failed_q.get() for _ in range(failed_q.qsize())]
+    # batches of 3, 3, 2 reads: the second one fails, whole and only
+    assert Engine.calls == 3
+    assert sorted(failed) == sorted(('device fell over', 'BaseCalled_template :: ' + n) for n in names[3:6])
