@@ -211,12 +211,13 @@ __device__ __forceinline__ double ev_sqrt(double y) {
 
 
 // sqrt of an integer-valued y in [0, 2^64): the seed is the hardware's 20-bit double rsqrt of y + 2^-60, which is y
-// itself for y >= 1 and keeps y = 0 finite, so that 0 comes out as 0 without a branch
+// itself for y >= 1 and keeps y = 0 finite, so that 0 comes out as 0 without a branch.  One Newton step takes the
+// seed to 2^-39, the closing step on s = y r squares that again: within an ulp of sqrt (checked against an 18-bit
+// seed of either sign of error)
 __device__ __forceinline__ double ev_sqrt_int(double y) {
   double r;
   asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(y + 0x1p-60));
   const double h = 0.5 * y;
-  r = r * fma(-h * r, r, 1.5);
   r = r * fma(-h * r, r, 1.5);
   const double s = y * r;
   return fma(fma(-s, s, y), 0.5 * r, s);
@@ -224,6 +225,7 @@ __device__ __forceinline__ double ev_sqrt_int(double y) {
 
 struct EvRead {       // per-read constants of the statistics
   double c_off;       // pivot - shift
+  double c0;          // (pivot - shift) / scale
   double inv_scale, inv_scale2, inv_scale_abs;
   double below_val, above_val;
   const double* rcp_tab;  // 1/n for n < 64
@@ -238,9 +240,9 @@ __device__ __forceinline__ void ev_base_stats(const EvRead& R, int n, long long 
   const double dnu = (double)nu;
   const double rn = n < 64 ? R.rcp_tab[n] : ev_rcp((double)n);
   const double sum_u = ((double)S1 + R.c_off * dnu) * R.inv_scale;
-  double sum_x = sum_u;
-  if (nl | nh) sum_x += (double)nl * R.below_val + (double)nh * R.above_val;
-  mean = sum_x * rn;
+  // every path gives a base without clipped samples the same bits: (S1 / n + pivot - shift) / scale, as the rounds do
+  if (nl | nh) mean = (sum_u + ((double)nl * R.below_val + (double)nh * R.above_val)) * rn;
+  else mean = fma((double)S1 * rn, R.inv_scale, R.c0);
   if (!R.compute_sd) return;
   double ss = 0.0;
   if (nu > 0) {
@@ -324,6 +326,54 @@ __device__ __forceinline__ int2 ev_loc_at(const EvLoc* locw, int sl) {  // pair 
   return *reinterpret_cast<const int2*>(reinterpret_cast<const char*>(locw) + sl * 8 + (sl >> 3) * 16);
 }
 
+// Deferred rounds.  A round of boundaries costs the same whether it resolves 32 of them or 3, and a 256-sample step
+// holds 29 on average: one step in five needed a second, nearly empty round.  While a read is in its plain stretch
+// (narrow range, interior steps, no clipped sample in the step or waiting in the current base) the prefixes of the
+// last two steps are therefore kept (a ring of 512 slots) and a round is only run when 32 boundaries wait, or when
+// some wait from the step before; what is left over is resolved together with the next step's.  Ring layout: lane t
+// of step s owns 48 bytes at ((s & 1) * 32 + t) * 48: eight 32-bit prefixes of d^2, then eight 16-bit prefixes of d
+// (at most 7 * 2047); its running prefix pair (low 32 bits of the sums since the read began) sits in a second array.
+// All arithmetic of such a round is modulo 2^32, exact while a base has at most 1 024 samples (1 024 * 2047^2 <
+// 2^32), which the distance test at the head of the step guarantees.
+#ifndef NRQ_EV_DEFER
+#define NRQ_EV_DEFER 1
+#endif
+#ifndef NRQ_EV_PIN
+#define NRQ_EV_PIN 1
+#endif
+constexpr int kEvArena = 3584;        // bytes of shared memory per warp
+constexpr int kEvRingG = 64 * 48;     // offset of the ring's running prefixes
+constexpr int kEvDeferReach = 768;    // a step defers only if the last resolved boundary lies at most this far behind it
+
+// the ring is addressed through one 32-bit shared-window address per warp (made opaque, so that it stays in a
+// register: left to itself the compiler re-forms the generic address, five instructions, at every use)
+template <int OFF>
+__device__ __forceinline__ unsigned ev_lds32(unsigned sa) {
+  unsigned v;
+  asm volatile("ld.shared.u32 %0, [%1+%2];" : "=r"(v) : "r"(sa), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ unsigned ev_lds16(unsigned sa) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(sa), "n"(OFF) : "memory");
+  return (unsigned)v;
+}
+template <int OFF>
+__device__ __forceinline__ uint2 ev_lds64(unsigned sa) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(sa), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ void ev_sts128(unsigned sa, unsigned x, unsigned y, unsigned z, unsigned w) {
+  asm volatile("st.shared.v4.u32 [%0+%1], {%2, %3, %4, %5};" ::"r"(sa), "n"(OFF), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+template <int OFF>
+__device__ __forceinline__ void ev_sts64(unsigned sa, unsigned x, unsigned y) {
+  asm volatile("st.shared.v2.u32 [%0+%1], {%2, %3};" ::"r"(sa), "n"(OFF), "r"(x), "r"(y) : "memory");
+}
+
 #ifndef NRQ_EV_AHEAD
 #define NRQ_EV_AHEAD 2
 #endif
@@ -340,8 +390,10 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
               double* __restrict__ norm_mean, double* __restrict__ norm_stdev,
               uint32_t* __restrict__ ev_start, uint32_t* __restrict__ ev_length) {
   __shared__ double rcp_tab[64];
-  __shared__ EvLoc loc[kEvWarps][32];                          // lane-local exclusive prefixes of (d, d^2)
-  __shared__ __align__(16) unsigned locc[kEvWarps][2][32][4];  // ... and of the packed clip counters
+  // per warp: lane-local exclusive prefixes of (d, d^2) (EvLoc[32], 2 560 bytes) and of the packed clip counters
+  // ([2][32][4] words, 1 024 bytes) of the current step -- or, while rounds are deferred (below), the prefixes of the
+  // last TWO steps in a compact form (64 x 48 bytes) and their lanes' running prefixes (64 x 8 bytes)
+  __shared__ __align__(16) unsigned char arena[kEvWarps][kEvArena];
   for (int i = threadIdx.x; i < 64; i += kEvWarps * 32) rcp_tab[i] = i ? 1.0 / (double)i : 0.0;
   __syncthreads();
   // broadcast from lane 0: tells the compiler that the warp index and everything loaded through it are
@@ -388,7 +440,10 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       off += (size_t)b0;
     }
   }
-  EvLoc* const locw = loc[warp];
+  EvLoc* const locw = reinterpret_cast<EvLoc*>(arena[warp]);
+  unsigned (*const locc)[32][4] = reinterpret_cast<unsigned (*)[32][4]>(arena[warp] + sizeof(EvLoc) * 32);
+  unsigned ring_sa = (unsigned)__cvta_generic_to_shared(arena[warp]);
+  asm volatile("" : "+r"(ring_sa));
   double* const o_mean = norm_mean + off;
   double* const o_sd = norm_stdev + off;
   uint32_t* const o_start = ev_start + off;
@@ -398,6 +453,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   EvRead R;
   R.c_off = __dsub_rn((double)pivot, coef.shift);
   R.inv_scale = 1.0 / coef.scale;
+  R.c0 = R.c_off * R.inv_scale;
   R.inv_scale2 = R.inv_scale * R.inv_scale;
   R.inv_scale_abs = fabs(R.inv_scale);
   R.below_val = k.below_val;
@@ -419,35 +475,167 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   unsigned long long run2 = 0, prev2 = 0;
   int runl = 0, runh = 0, prevl = 0, prevh = 0;
   int cur = 0;      // next boundary to resolve (0 .. nb)
-  int prevpos = 0;  // position of boundary cur - 1
-  // position of boundary cur + lane: np.split(norm_signal, new_segs[1:-1]) -- the first piece starts at 0, the
+  // Boundary positions are kept as SLOTS (position + a, the coordinate the steps are laid out in): every round
+  // compares them with step limits and indexes the step's prefixes by them.
+  const int adj = a - seg0;  // slot of a boundary = new_segs value + adj
+  // the lane's own views of the two arrays the steps read, pinned in vector registers: as warp-uniform bases the
+  // compiler keeps them on the uniform datapath and re-forms each address from there (seven instructions a load)
+#if NRQ_EV_PIN & 1
+  const int32_t* segs_l = segs + lane;
+  asm volatile("" : "+l"(segs_l));
+#else
+  const int32_t* const segs_l = segs + lane;
+#endif
+#if NRQ_EV_PIN & 2
+  const int16_t* base_l = base_al + 8 * lane;
+  asm volatile("" : "+l"(base_l));
+#else
+  const int16_t* const base_l = base_al + 8 * lane;
+#endif
+  int prevpos = a;  // slot of boundary cur - 1
+  // slot of boundary cur + lane: np.split(norm_signal, new_segs[1:-1]) -- the first piece starts at 0, the
   // last runs to the end (:64).  Loaded as soon as cur is known, a step ahead of its use.
   auto load_pos = [&](int c) {  // c > 0 (cur only grows, and boundary 0 is the first one resolved)
     const unsigned bidx = (unsigned)(c + lane);
-    int q = bidx == (unsigned)nb ? n_norm : kNoPos;
-    if (bidx < (unsigned)nb) q = __ldg(segs + bidx) - seg0;
+    int q = bidx == (unsigned)nb ? n_norm + a : kNoPos;
+    if (bidx < (unsigned)nb) q = __ldg(segs_l + (unsigned)c) + adj;
     return q;
   };
   int pos = load_pos(0);
-  if (lane == 0) pos = 0;  // boundary 0 sits at sample 0 whatever new_segs[0] says
+  if (lane == 0) pos = a;  // boundary 0 sits at sample 0 whatever new_segs[0] says
   // interior steps (all 256 samples belong to the read) of a read with a narrow unclipped range: [fast_lo, fast_hi)
   const int fast_lo = narrow ? ((a + kSub - 1) / kSub) * kSub : 0x7fffffff;
   const int fast_hi = n_norm + a - kSub + 1;
 
+  bool dpend = false;  // boundaries of the step before may still wait in the ring
+  unsigned pe1 = 0u, pe2 = 0u;  // while they may: low words of the prefixes at the last resolved boundary
   for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
     const int slot = tile0 + 8 * lane;
-    // ================= fast step: interior step of a read with a narrow unclipped range =================
-    if (tile0 >= fast_lo && tile0 < fast_hi) {
-      const int4 q = __ldg(reinterpret_cast<const int4*>(base_al + slot));
+    const bool fast = tile0 >= fast_lo && tile0 < fast_hi;  // interior step of a read with a narrow unclipped range
+    int4 q = make_int4(0, 0, 0, 0);
+    bool ds = false;  // this step's rounds may be deferred
+    int dtot1 = 0;
+    unsigned dtot2 = 0;
+    if (fast) {
+      q = __ldg(reinterpret_cast<const int4*>(base_l + (unsigned)tile0));
       // the samples two steps ahead start their trip from HBM now (no register held for them)
       if (slot + kEvAhead * kSub + 8 <= n_norm)
-        asm volatile("prefetch.global.L1 [%0];" ::"l"(base_al + slot + kEvAhead * kSub));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(base_l + (unsigned)tile0 + kEvAhead * kSub));
+      if (NRQ_EV_DEFER && tiny) {  // optimistic: no clipped sample in the step, d = code - u_lo needs no select
+        int l1[8];
+        unsigned l2[8];
+        int s1 = 0;
+        unsigned s2 = 0;
+        bool oor = false;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned d = (unsigned)(unpack16(q, j) - u_lo);
+          oor |= d > range;
+          l1[j] = s1;
+          l2[j] = s2;
+          s1 += (int)d;
+          s2 += d * d;
+        }
+        ds = !__any_sync(0xffffffffu, oor) && cur >= 2 && runl == prevl && runh == prevh &&
+             tile0 - prevpos <= kEvDeferReach;
+        if (ds) {
+          const unsigned rl = (unsigned)((tile0 >> 3) & 32) + (unsigned)lane;  // the lane's place in the ring
+          const unsigned mine = ring_sa + rl * 48u;
+          ev_sts128<0>(mine, l2[0], l2[1], l2[2], l2[3]);
+          ev_sts128<16>(mine, l2[4], l2[5], l2[6], l2[7]);
+          ev_sts128<32>(mine, (unsigned)l1[0] | ((unsigned)l1[1] << 16), (unsigned)l1[2] | ((unsigned)l1[3] << 16),
+                        (unsigned)l1[4] | ((unsigned)l1[5] << 16), (unsigned)l1[6] | ((unsigned)l1[7] << 16));
+          int i1 = s1;
+          unsigned i2 = s2;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) ev_scan_step(i1, i2, o);
+          ev_sts64<kEvRingG>(ring_sa + rl * 8u, (unsigned)run1 + (unsigned)(i1 - s1), (unsigned)run2 + (i2 - s2));
+          if (!dpend) { pe1 = (unsigned)prev1; pe2 = (unsigned)prev2; }
+          dtot1 = __shfl_sync(0xffffffffu, i1, 31);
+          dtot2 = __shfl_sync(0xffffffffu, i2, 31);
+          __syncwarp();
+        }
+      }
+    }
+    // ================= rounds over the ring: this step's (deferred where possible), or what the step before left =====
+    if (ds || dpend) {
+      const int limit = ds ? tile0 + kSub : tile0;
+      for (;;) {
+        const int gs = pos;
+        const bool inb = gs < limit;
+        const unsigned bal = __ballot_sync(0xffffffffu, inb);
+        if (bal == 0u) break;
+        // fewer than 32 to resolve: they wait for the next step's, unless some (lane 0's is the oldest) wait already
+        if (ds && bal != 0xffffffffu && __shfl_sync(0xffffffffu, gs, 0) >= tile0) break;
+        const int cntb = __popc(bal);
+        const unsigned sl = (unsigned)gs & 511u;
+        const unsigned t8 = sl & 0x1f8u;  // 8 x (place in the ring)
+        const unsigned L2 = ev_lds32<0>(ring_sa + sl * 4u + t8 * 2u);
+        const unsigned L1 = ev_lds16<32>(ring_sa + sl * 2u + t8 * 4u);
+        const uint2 G = ev_lds64<kEvRingG>(ring_sa + t8);
+        const unsigned E1 = G.x + L1;
+        const unsigned E2 = G.y + L2;
+        unsigned pE1 = __shfl_up_sync(0xffffffffu, E1, 1);
+        unsigned pE2 = __shfl_up_sync(0xffffffffu, E2, 1);
+        int bpos = __shfl_up_sync(0xffffffffu, pos, 1);
+        if (lane == 0) { pE1 = pe1; pE2 = pe2; bpos = prevpos; }
+        if (inb) {
+          const int n = pos - bpos;
+          const int S1 = (int)(E1 - pE1);  // 0 <= S1 <= S2 < 2^32: d is a non-negative integer
+          const unsigned S2 = E2 - pE2;
+#ifdef NRQ_EV_NOSTAT  // diagnostic build: the round's memory traffic without its arithmetic
+          const unsigned o_ = (unsigned)(cur + lane - 1);
+          o_mean[o_] = __hiloint2double(S1, n);
+          o_sd[o_] = __hiloint2double((int)S2, n);
+          o_start[o_] = (uint32_t)(bpos - adj);
+          o_length[o_] = (uint32_t)n;
+          if (false) {
+#endif
+          const double dn = (double)n;
+          const double rn = ev_rcp(dn);
+          // mean = (S1 / n + pivot - shift) / scale
+          double mean = fma((double)S1 * rn, R.inv_scale, R.c0), sd = qnan;
+          if (R.compute_sd) {
+            const unsigned long long num =
+                (unsigned long long)(unsigned)n * (unsigned long long)S2 - (unsigned long long)((long long)S1 * (long long)S1);
+            sd = ev_sqrt_int((double)num) * (rn * R.inv_scale_abs);  // sqrt(num / n^2 / scale^2)
+          }
+          if (n <= 0) { mean = qnan; sd = qnan; }
+          const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
+          o_mean[o] = mean;
+          o_sd[o] = sd;
+          o_start[o] = (uint32_t)(bpos - adj);
+          o_length[o] = (uint32_t)n;
+#ifdef NRQ_EV_NOSTAT
+          }
+#endif
+        }
+        pe1 = __shfl_sync(0xffffffffu, E1, cntb - 1);
+        pe2 = __shfl_sync(0xffffffffu, E2, cntb - 1);
+        prevpos = __shfl_sync(0xffffffffu, pos, cntb - 1);
+        cur += cntb;
+        pos = load_pos(cur);
+      }
+      if (ds) {
+        run1 += dtot1;
+        run2 += dtot2;
+        dpend = true;
+        continue;
+      }
+      // back to 64-bit prefixes: the last resolved boundary lies before this step's first sample, at most 1 024
+      // samples before it, so the distances are the differences of the low words, taken as unsigned
+      dpend = false;
+      prev1 = run1 - (long long)(unsigned long long)((unsigned)run1 - pe1);
+      prev2 = run2 - (unsigned long long)((unsigned)run2 - pe2);
+    }
+    // ================= fast step: interior step of a read with a narrow unclipped range =================
+    if (fast) {
       int l1[8];
       unsigned l2[8];
       int s1 = 0;
       unsigned s2 = 0, cnt = 0;
       bool anyc = true;
-      if (tiny) {  // optimistic: no clipped sample in the step, d = code - u_lo needs no select
+      if (!NRQ_EV_DEFER && tiny) {  // optimistic: no clipped sample in the step, d = code - u_lo needs no select
         bool oor = false;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -485,8 +673,8 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             lc[j] = cnt;
             cnt += (v < u_lo ? 1u : 0u) + (v > u_hi ? 65536u : 0u);
           }
-          *reinterpret_cast<uint4*>(locc[warp][0][lane]) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
-          *reinterpret_cast<uint4*>(locc[warp][1][lane]) = make_uint4(lc[4], lc[5], lc[6], lc[7]);
+          *reinterpret_cast<uint4*>(locc[0][lane]) = make_uint4(lc[0], lc[1], lc[2], lc[3]);
+          *reinterpret_cast<uint4*>(locc[1][lane]) = make_uint4(lc[4], lc[5], lc[6], lc[7]);
         }
       }
       {
@@ -514,11 +702,11 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       __syncwarp();
       const int tile_end = tile0 + kSub;
       for (;;) {
-        const bool inb = pos + a < tile_end;
+        const bool inb = pos < tile_end;
         const unsigned bal = __ballot_sync(0xffffffffu, inb);
         const int cntb = __popc(bal);
         if (cntb == 0) break;
-        const int sl = (pos + a - tile0) & (kSub - 1);
+        const int sl = (pos - tile0) & (kSub - 1);
         const int t = sl >> 3;
         const int2 L = ev_loc_at(locw, sl);
         const int E1 = __shfl_sync(0xffffffffu, ex1, t) + L.x;
@@ -536,7 +724,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         // bits; the clipped samples of each base are differences of the packed (below, above) counter prefixes, and
         // only a base that holds one takes the general statistics
         if (anyc && cur >= 2 && cur + 32 < nb && c_small) {
-          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][(sl & 7) >> 2][t][sl & 3];
+          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[(sl & 7) >> 2][t][sl & 3];
           const unsigned pEC = __shfl_up_sync(0xffffffffu, EC, 1);
           int nl = (int)(EC & 0xffffu), nh = (int)(EC >> 16);
           if (lane == 0) {  // the base may have begun in an earlier step
@@ -556,8 +744,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
               if ((nl | nh) == 0) {
                 const double dn = (double)n;
                 const double rn = ev_rcp(dn);
-                const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
-                mean = sum_u * rn;
+                mean = fma((double)S1 * rn, R.inv_scale, R.c0);
                 if (R.compute_sd) {
                   const unsigned long long num = (unsigned long long)(unsigned)n * (unsigned long long)S2 -
                                                  (unsigned long long)((long long)S1 * (long long)S1);
@@ -570,7 +757,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const unsigned o = (unsigned)(cur + lane - 1);
             o_mean[o] = mean;
             o_sd[o] = sd;
-            o_start[o] = (uint32_t)(bpos + seg0);
+            o_start[o] = (uint32_t)(bpos - adj);
             o_length[o] = (uint32_t)n;
           }
           const unsigned last = __shfl_sync(0xffffffffu, EC, cntb - 1);
@@ -593,8 +780,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const unsigned S2 = E2 - pE2;
             const double dn = (double)n;
             const double rn = ev_rcp(dn);
-            const double sum_u = ((double)S1 + R.c_off * dn) * R.inv_scale;
-            double mean = sum_u * rn, sd = qnan;
+            double mean = fma((double)S1 * rn, R.inv_scale, R.c0), sd = qnan;
             if (R.compute_sd) {
               const unsigned long long num =
                   (unsigned long long)(unsigned)n * (unsigned long long)S2 - (unsigned long long)((long long)S1 * (long long)S1);
@@ -604,7 +790,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
             const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
             o_mean[o] = mean;
             o_sd[o] = sd;
-            o_start[o] = (uint32_t)(bpos + seg0);
+            o_start[o] = (uint32_t)(bpos - adj);
             o_length[o] = (uint32_t)n;
           }
           prev1 = run1 + __shfl_sync(0xffffffffu, E1, cntb - 1);
@@ -619,7 +805,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         const int bidx = cur + lane;
         int el = runl, eh = runh, pl = runl, ph = runh;
         if (anyc) {
-          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[warp][(sl & 7) >> 2][t][sl & 3];
+          const unsigned EC = __shfl_sync(0xffffffffu, exc, t) + locc[(sl & 7) >> 2][t][sl & 3];
           el += (int)(EC & 0xffffu);
           eh += (int)(EC >> 16);
           pl = __shfl_up_sync(0xffffffffu, el, 1);
@@ -628,9 +814,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         if (inb && bidx >= 1) {
           const int kbase = bidx - 1;
           const int s_hi = segs[bidx] - seg0;
-          const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos);
+          const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos - a);
           const int pos0 = (kbase == 0) ? 0 : s_lo;
-          const int n = pos - pos0;
+          const int n = pos - a - pos0;
           double mean = qnan, sd = qnan;
           if (n > 0) {
             long long S1;
@@ -669,7 +855,6 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
     }
     // ================= general step =================
     // ---- load 8 samples, lane totals
-    int4 q = make_int4(0, 0, 0, 0);
     if (slot < n_norm + a) {
       const int16_t* ptr = base_al + slot;
       if (ptr >= b.raw && ptr + 8 <= raw_end) q = __ldg(reinterpret_cast<const int4*>(ptr));
@@ -710,11 +895,11 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
     const int tile_end = tile0 + kSub;
     for (;;) {
       const int bidx = cur + lane;
-      const bool inb = pos + a < tile_end;
+      const bool inb = pos < tile_end;
       const unsigned bal = __ballot_sync(0xffffffffu, inb);
       const int cntb = __popc(bal);
       if (cntb == 0) break;
-      int sl = inb ? pos + a - tile0 : 0;  // slot inside the step
+      int sl = inb ? pos - tile0 : 0;  // slot inside the step
       if (sl < 0) sl = 0;
       const int t = sl >> 3, jn = sl & 7;
       int4 qq;
@@ -746,9 +931,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       if (inb && bidx >= 1) {
         const int kbase = bidx - 1;
         const int s_hi = segs[bidx] - seg0;
-        const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos);
+        const int s_lo = (lane == 0) ? segs[kbase] - seg0 : (kbase == 0 ? segs[0] - seg0 : bpos - a);
         const int pos0 = (kbase == 0) ? 0 : s_lo;
-        const int n = pos - pos0;
+        const int n = pos - a - pos0;
         double mean = qnan, sd = qnan;
         if (n > 0) ev_base_stats(R, n, e1 - b1, e2 - b2, el - bl, eh - bh, mean, sd);
         norm_mean[off + kbase] = mean;
