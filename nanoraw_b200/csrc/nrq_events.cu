@@ -338,9 +338,7 @@ __device__ __forceinline__ int2 ev_loc_at(const EvLoc* locw, int sl) {  // pair 
 #ifndef NRQ_EV_DEFER
 #define NRQ_EV_DEFER 1
 #endif
-#ifndef NRQ_EV_PIN
-#define NRQ_EV_PIN 1
-#endif
+
 constexpr int kEvArena = 3584;        // bytes of shared memory per warp
 constexpr int kEvRingG = 64 * 48;     // offset of the ring's running prefixes
 constexpr int kEvDeferReach = 768;    // a step defers only if the last resolved boundary lies at most this far behind it
@@ -478,20 +476,13 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   // Boundary positions are kept as SLOTS (position + a, the coordinate the steps are laid out in): every round
   // compares them with step limits and indexes the step's prefixes by them.
   const int adj = a - seg0;  // slot of a boundary = new_segs value + adj
-  // the lane's own views of the two arrays the steps read, pinned in vector registers: as warp-uniform bases the
-  // compiler keeps them on the uniform datapath and re-forms each address from there (seven instructions a load)
-#if NRQ_EV_PIN & 1
+  // the lane's own view of the boundaries, pinned in a vector register pair: as a warp-uniform base the compiler
+  // keeps it on the uniform datapath and re-forms the address from there (seven instructions a load).  The same
+  // for the samples or the four output columns costs registers the kernel does not have at 48 warps per SM
+  // (measured: 12.4-12.9 ms against 11.8; at 48 registers / 42 warps 12.6 ms without any pinning).
   const int32_t* segs_l = segs + lane;
   asm volatile("" : "+l"(segs_l));
-#else
-  const int32_t* const segs_l = segs + lane;
-#endif
-#if NRQ_EV_PIN & 2
-  const int16_t* base_l = base_al + 8 * lane;
-  asm volatile("" : "+l"(base_l));
-#else
   const int16_t* const base_l = base_al + 8 * lane;
-#endif
   int prevpos = a;  // slot of boundary cur - 1
   // slot of boundary cur + lane: np.split(norm_signal, new_segs[1:-1]) -- the first piece starts at 0, the
   // last runs to the end (:64).  Loaded as soon as cur is known, a step ahead of its use.

@@ -96,10 +96,26 @@ struct SpecSm {
 
 // Sort bin of a task: tasks of one batch run in lock-step, so they should need the same number of selection rounds
 // (K, major) and about the same number of samples (four classes of samples per change-point, minor); bin 0 first.
-__device__ __forceinline__ int spec_bin(unsigned pk) {
+#ifndef NRQ_SPEC_BINS
+#define NRQ_SPEC_BINS 2
+#endif
+__device__ __forceinline__ int spec_bin(unsigned pk, int off) {  // off: samples of the region's first 16-byte word before it
   const int n = (int)(pk & 255u), K = (int)((pk >> 8) & 63u);
   const int cls = min(3, max(0, (n - 4 * (K + 2)) / (2 * (K + 2))));
+#if NRQ_SPEC_BINS == 2
+  // K <= 15 (nearly all tasks): one bin per (K, key blocks of the region), so that the lanes of a batch run the same
+  // number of cumulative-sum steps and scan the same number of block maxima; above that K in fours with the classes
+  if (K > 15) return ((kSpecMaxK - K) >> 2) * 4 + (3 - cls);                     // 0 .. 47
+  const int nb = min(12, (n - 2 * kSpecM + 1 + 7) >> 3);                          // 1 .. 12
+  return 48 + (15 - K) * 12 + (12 - nb);                                          // 48 .. 227
+#elif NRQ_SPEC_BINS == 3
+  // ... or per (K, 16-byte words the lane reads): a word costs more than a key block
+  if (K > 15) return ((kSpecMaxK - K) >> 2) * 4 + (3 - cls);
+  const int nw = min(13, max(2, (n + off + 7) >> 3));                             // 2 .. 13
+  return 48 + (15 - K) * 12 + (13 - nw);
+#else
   return (kSpecMaxK - K) * 4 + (3 - cls);
+#endif
 }
 
 // a code outside a table that does not span the clip limits: the division itself (rare; kept out of line)
@@ -328,6 +344,7 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
     if (status[r] != NRQ_ST_OK) continue;
     const ReadGeom g = read_geom(b, r);
     const int last = g.n_starts - 1;
+    const int sig_al = (int)((reinterpret_cast<uintptr_t>(g.sig) >> 1) & 7u);
     const int32_t* t = g.starts;
     const NormCoef coef = load_coef(sv, r);
     const int64_t ioff = indel_off[r];
@@ -374,7 +391,8 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         for (;;) {
         for (int k = tid; k < 256; k += kSpecThreads) sm.hist[k] = 0;
         __syncthreads();
-        for (int i = tid; i < nt; i += kSpecThreads) atomicAdd(&sm.hist[spec_bin(sm.task[i].pk)], 1);
+        for (int i = tid; i < nt; i += kSpecThreads)
+          atomicAdd(&sm.hist[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1);
         __syncthreads();
         if (warp == 0) {
           int v[8], s = 0;
@@ -392,7 +410,7 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         }
         __syncthreads();
         for (int i = tid; i < nt; i += kSpecThreads)
-          sm.order[atomicAdd(&sm.hist[spec_bin(sm.task[i].pk)], 1)] = (unsigned short)i;
+          sm.order[atomicAdd(&sm.hist[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1)] = (unsigned short)i;
         if (tid == 0) { sm.cursor = 0; sm.n_retry = 0; }
         __syncthreads();
         for (;;) {
