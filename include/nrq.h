@@ -72,7 +72,11 @@ typedef struct nrq_params {
   int32_t debug_flags;      /* bit0: force the general (bisection) order-statistic path in nrq_norm_stats;
                                bit1: event statistics in numpy's float64 summation order (bit-identical to
                                numpy, slower) instead of exact integer prefix sums (within a few ulps);
-                               bit2: no speculative first search in nrq_resegment (walk only; same results, slower) */
+                               bit2: no speculative first search in nrq_resegment (walk only; same results, slower);
+                               bit4 / bit5 (experiments with the stage's two kernels on different streams,
+                               profiles/overlap_probe2.py): nrq_resegment runs only its first kernel (the speculative
+                               searches) / only its second (the walk, trusting the entries a bit-4 call over the
+                               same reads left in spec_scratch) */
 } nrq_params;
 
 /* Ragged batch, inputs.  R = n_reads.

@@ -80,7 +80,16 @@ const DeviceGrids& device_grids() {
 }
 
 int resegment_grid(int n_reads) {
-  const int cached = device_grids().seg;
+  int cached = device_grids().seg;
+  // NRQ_SEG_CTAS_PER_SM (experiments: the walk sharing the SMs with another kernel): fewer resident CTAs per SM
+  const char* env = getenv("NRQ_SEG_CTAS_PER_SM");
+  const int limit = env ? atoi(env) : 0;
+  if (limit > 0) {
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (limit * sms < cached) cached = limit * sms;
+  }
   int need = (n_reads + nrq::kSegWarps - 1) / nrq::kSegWarps;
   return need < cached ? (need > 0 ? need : 1) : cached;
 }
@@ -260,13 +269,16 @@ static int resegment_impl(const nrq_batch* b, const nrq_params* p, const double*
   // spec_scratch: an int2 entry per indel, then kSpecCptBytesPerIndel bytes per indel for the found change-points
   int2* spec_entries = reinterpret_cast<int2*>(spec_scratch);
   unsigned char* spec_bytes = reinterpret_cast<unsigned char*>(spec_scratch) + 8 * spec_capacity;
-  if (speculate) {
+  // debug_flags bit 4 / bit 5 (experiments with the two kernels on different streams): only the first / only the
+  // second kernel of the stage (the second then trusts the entries a bit-4 call left in spec_scratch)
+  if (speculate && !(p->debug_flags & 32)) {
     nrq::k_speculate<<<speculate_grid(b->n_reads), nrq::kSpecThreads, sizeof(nrq::SpecSm), s>>>(
         *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), work_counter + 1, status,
         spec_entries, spec_bytes);
     NRQ_CHECK_LAUNCH("k_speculate");
   }
   if (mid) cudaEventRecord(mid, s);
+  if (p->debug_flags & 16) return 0;
   nrq::k_resegment<<<grid, nrq::kSegWarps * 32, 0, s>>>(
       *b, *p, scale_values, indel_off, reinterpret_cast<const int4*>(indels), n_bases,
       reinterpret_cast<int4*>(group_scratch), big_scratch, work_counter, status, new_segs, region_samples,

@@ -123,3 +123,107 @@ def test_translation_and_power_of_two_scaling_invariance(engine, reads, result):
         for other in (rm.events_of(r), rd2.events_of(r)):
             assert np.max(np.abs(other['norm_mean'] - ev['norm_mean'])) < 1e-12
             assert np.max(np.abs(other['norm_stdev'] - ev['norm_stdev'])) < 1e-11
+
+
+def test_event_table_on_hand_made_segmentations(engine):
+    """k_event_table keeps the prefixes of the last two 256-sample steps and resolves a round of boundaries only
+    when 32 wait (or when some wait from the step before); it falls back to its step-by-step paths around clipped
+    samples, bases of more than 768 samples and the ends of the read.  Segmentations made to sit on those seams --
+    bursts of one- to three-sample bases (more than 32 boundaries per step for many steps), bases of hundreds to
+    thousands of samples, spikes beside both -- must give the numpy-order kernel's table: start / length exactly,
+    mean / sd within the contract (resquiggle.py:60-70)."""
+    import ctypes as C
+    import torch
+    from nanoraw_b200 import _lib
+    from nanoraw_b200.engine import DeviceResults, ResquiggleParams, _ptr
+    cfg = synth.SynthConfig(span_mean=9000, span_sd=300, seed_base=64000)
+    genome = synth.make_genome(1_000_000, seed=19)
+    reads = [synth.make_read(genome, synth.kmer_levels(cfg), cfg, i) for i in range(12)]
+    rng = np.random.default_rng(5)
+    for rd in reads:  # spikes: isolated ones and short runs, some at the very ends of the read's samples
+        raw = rd.raw.astype(np.int32)
+        n = int(rd.starts[-1])
+        r0 = int(rd.read_start_rel_to_raw)
+        where = np.concatenate([rng.integers(0, n, 40), [0, 1, n - 1, n - 2], rng.integers(0, n - 8, 6)[:, None].repeat(5, 1).ravel()
+                                + np.tile(np.arange(5), 6)])
+        raw[r0 + where] += rng.choice([-3000, 3000], len(where))
+        rd.raw = np.clip(raw, -32768, 32767).astype(np.int16)
+    hb = ReadBatch.from_reads(reads)
+    db = engine.upload(hb)
+    pc = ResquiggleParams().to_c()
+    out = DeviceResults(db.n_reads, db.total_align, engine.device)
+    ws = engine.workspace(db.n_reads, db.total_align, pc)
+    engine.run_device(db, pc, out=out, workspace=ws)
+    torch.cuda.synchronize()
+    assert bool((out.status[:db.n_reads] == 0).all())
+    align_off = np.asarray(hb.align_off)
+    segs = out.new_segs.cpu().numpy()
+    n_bases = out.n_bases.cpu().numpy()
+
+    def pattern(kind, n_samples, cap):
+        """boundaries 0 = b[0] < b[1] < ... <= n_samples, at most cap bases"""
+        b = [0]
+        while b[-1] < n_samples and len(b) <= cap:
+            left = n_samples - b[-1]
+            budget = cap + 1 - len(b)
+            if budget * 3000 < left:  # running out of bases: stride to the end
+                b.append(b[-1] + min(left, 3000))
+                continue
+            mode = kind if kind != 'mix' else rng.choice(['burst', 'long', 'plain', 'edge'])
+            if mode == 'burst':      # > 32 boundaries per 256-sample step, for a few steps
+                d = rng.integers(1, 4, int(rng.integers(40, 400)))
+            elif mode == 'long':     # around the 768-sample reach and the 1 024-sample limit of the 32-bit sums
+                d = rng.choice([500, 700, 767, 768, 769, 1000, 1023, 1024, 1025, 1300, 2600], 1)
+            elif mode == 'edge':     # boundaries on and beside the step edges
+                base = (b[-1] // 256 + 1) * 256
+                d = np.diff(np.concatenate([[b[-1]], base + np.array([-1, 0, 1, 255, 256, 257, 511, 513])]))
+                d = d[d > 0]
+            else:
+                d = rng.geometric(1 / 7.9, int(rng.integers(20, 300))) + 1
+            before = len(b)
+            for step in d:
+                if b[-1] + step > n_samples or len(b) > cap:
+                    break
+                b.append(int(b[-1] + step))
+            if len(b) == before:     # nothing of this kind fits any more: one last base to the end
+                b.append(n_samples)
+        return np.array(b[:cap + 1], dtype=np.int32)
+
+    kinds = ['mix', 'burst', 'long', 'edge', 'plain', 'mix']
+    new_nb = n_bases.copy()
+    for r in range(db.n_reads):
+        a0, a1 = int(align_off[r]), int(align_off[r + 1])
+        cap = a1 - a0 - 1
+        bnd = pattern(kinds[r % len(kinds)], int(reads[r].starts[-1]), cap)
+        nb = len(bnd) - 1
+        assert 2 <= nb <= cap
+        segs[a0 + r:a0 + r + nb + 1] = bnd
+        new_nb[r] = nb
+    out.new_segs.copy_(torch.from_numpy(segs))
+    out.n_bases.copy_(torch.from_numpy(new_nb))
+
+    tables = {}
+    for flags in (0, 2):
+        p = ResquiggleParams().to_c()
+        p.debug_flags = flags
+        o = DeviceResults(db.n_reads, db.total_align, engine.device)
+        for name in ('norm_mean', 'norm_stdev'):
+            getattr(o, name).fill_(-77.0)
+        rc = engine.lib.nrq_event_table(C.byref(db.c), C.byref(p), _ptr(out.scale_values), _ptr(out.n_bases),
+                                        _ptr(out.new_segs), _ptr(out.status), _ptr(o.norm_mean), _ptr(o.norm_stdev),
+                                        _ptr(o.ev_start), _ptr(o.ev_length), _ptr(o.ev_base), engine._stream())
+        _lib.check(rc, 'nrq_event_table')
+        torch.cuda.synchronize()
+        tables[flags] = {k: getattr(o, k).cpu().numpy() for k in ('norm_mean', 'norm_stdev', 'ev_start', 'ev_length')}
+    fast, exact = tables[0], tables[2]
+    for r in range(db.n_reads):
+        a0 = int(align_off[r])
+        nb = int(new_nb[r])
+        sl = slice(a0, a0 + nb)
+        bnd = segs[a0 + r:a0 + r + nb + 1]
+        assert np.array_equal(fast['ev_start'][sl], bnd[:-1]) and np.array_equal(exact['ev_start'][sl], bnd[:-1])
+        assert np.array_equal(fast['ev_length'][sl], np.diff(bnd)) and np.array_equal(exact['ev_length'][sl], np.diff(bnd))
+        for col, tol in (('norm_mean', 1e-12), ('norm_stdev', 1e-10)):
+            a, b = fast[col][sl], exact[col][sl]
+            assert not np.isnan(b).any()
+            assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < tol, (r, kinds[r % len(kinds)], col)
