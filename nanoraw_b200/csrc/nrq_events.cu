@@ -381,7 +381,9 @@ constexpr int kEvPartSamples = 65536;   // ... of about this many samples each
 constexpr int kNoPos = 0x3fffffff;
   // "no such boundary": never inside a step
 
-template <bool PARTS>  // PARTS: long reads are streamed in gridDim.y parts (nrq_params.long_read_parts)
+// PARTS: long reads are streamed in gridDim.y parts (nrq_params.long_read_parts).  (compute_sd as a second template
+// parameter takes a test and a branch out of every round and costs more than that in spills: 11.77 against 11.68 ms)
+template <bool PARTS>
 __global__ void __launch_bounds__(kEvWarps * 32, NRQ_EV_MINB)
 k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int32_t* __restrict__ n_bases,
               const int32_t* __restrict__ new_segs, const int32_t* __restrict__ status,
@@ -499,14 +501,15 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
   const int fast_hi = n_norm + a - kSub + 1;
 
   bool dpend = false;  // boundaries of the step before may still wait in the ring
+  // no clipped sample waits in the current base and boundary 1 is behind us: settled at the end of every step that
+  // is not deferred (a deferred step changes none of it)
+  bool calm = false;
   unsigned pe1 = 0u, pe2 = 0u;  // while they may: low words of the prefixes at the last resolved boundary
   for (int tile0 = 0; tile0 <= n_norm + a; tile0 += kSub) {
     const int slot = tile0 + 8 * lane;
     const bool fast = tile0 >= fast_lo && tile0 < fast_hi;  // interior step of a read with a narrow unclipped range
     int4 q = make_int4(0, 0, 0, 0);
     bool ds = false;  // this step's rounds may be deferred
-    int dtot1 = 0;
-    unsigned dtot2 = 0;
     if (fast) {
       q = __ldg(reinterpret_cast<const int4*>(base_l + (unsigned)tile0));
       // the samples two steps ahead start their trip from HBM now (no register held for them)
@@ -527,8 +530,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           s1 += (int)d;
           s2 += d * d;
         }
-        ds = !__any_sync(0xffffffffu, oor) && cur >= 2 && runl == prevl && runh == prevh &&
-             tile0 - prevpos <= kEvDeferReach;
+        ds = !__any_sync(0xffffffffu, oor) && calm && tile0 - prevpos <= kEvDeferReach;
         if (ds) {
           const unsigned rl = (unsigned)((tile0 >> 3) & 32) + (unsigned)lane;  // the lane's place in the ring
           const unsigned mine = ring_sa + rl * 48u;
@@ -542,8 +544,9 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           for (int o = 1; o < 32; o <<= 1) ev_scan_step(i1, i2, o);
           ev_sts64<kEvRingG>(ring_sa + rl * 8u, (unsigned)run1 + (unsigned)(i1 - s1), (unsigned)run2 + (i2 - s2));
           if (!dpend) { pe1 = (unsigned)prev1; pe2 = (unsigned)prev2; }
-          dtot1 = __shfl_sync(0xffffffffu, i1, 31);
-          dtot2 = __shfl_sync(0xffffffffu, i2, 31);
+          // (the rounds below work on the ring and the low words alone: the running sums can move on now)
+          run1 += __shfl_sync(0xffffffffu, i1, 31);
+          run2 += __shfl_sync(0xffffffffu, i2, 31);
           __syncwarp();
         }
       }
@@ -574,14 +577,6 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           const int n = pos - bpos;
           const int S1 = (int)(E1 - pE1);  // 0 <= S1 <= S2 < 2^32: d is a non-negative integer
           const unsigned S2 = E2 - pE2;
-#ifdef NRQ_EV_NOSTAT  // diagnostic build: the round's memory traffic without its arithmetic
-          const unsigned o_ = (unsigned)(cur + lane - 1);
-          o_mean[o_] = __hiloint2double(S1, n);
-          o_sd[o_] = __hiloint2double((int)S2, n);
-          o_start[o_] = (uint32_t)(bpos - adj);
-          o_length[o_] = (uint32_t)n;
-          if (false) {
-#endif
           const double dn = (double)n;
           const double rn = ev_rcp(dn);
           // mean = (S1 / n + pivot - shift) / scale
@@ -597,9 +592,6 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           o_sd[o] = sd;
           o_start[o] = (uint32_t)(bpos - adj);
           o_length[o] = (uint32_t)n;
-#ifdef NRQ_EV_NOSTAT
-          }
-#endif
         }
         pe1 = __shfl_sync(0xffffffffu, E1, cntb - 1);
         pe2 = __shfl_sync(0xffffffffu, E2, cntb - 1);
@@ -608,8 +600,6 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
         pos = load_pos(cur);
       }
       if (ds) {
-        run1 += dtot1;
-        run2 += dtot2;
         dpend = true;
         continue;
       }
@@ -841,6 +831,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
       run2 += tot2;
       runl += (int)(totc & 0xffffu);
       runh += (int)(totc >> 16);
+      calm = cur >= 2 && runl == prevl && runh == prevh;
       __syncwarp();
       continue;
     }
@@ -946,6 +937,7 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
     run2 += tot2;
     runl += (int)(totc & 0xffffu);
     runh += (int)(totc >> 16);
+    calm = cur >= 2 && runl == prevl && runh == prevh;
   }
 }
 
