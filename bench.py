@@ -438,7 +438,7 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
-TRAFFIC_FILE = 'r2z_traffic_100k.json'
+TRAFFIC_FILE = 'r3z_traffic_100k.json'
 STAGE_KERNELS = {'k_align_scan': ('k_align_count', 'k_scan_counts', 'k_align_fill'), 'k_norm_stats': ('k_norm_stats',),
                  'k_resegment': ('k_speculate', 'k_resegment'), 'k_event_table': ('k_event_table',)}
 

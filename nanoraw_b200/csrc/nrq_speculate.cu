@@ -33,7 +33,7 @@ namespace nrq {
 #define NRQ_SPEC_POOL 768
 #endif
 #ifndef NRQ_SPEC_SLAB
-#define NRQ_SPEC_SLAB 1152
+#define NRQ_SPEC_SLAB 1376
 #endif
 #ifndef NRQ_SPEC_MINB
 #define NRQ_SPEC_MINB 2
@@ -71,19 +71,36 @@ __host__ __device__ __forceinline__ int spec_word(int flag, int K, int start, in
   return flag | (K << 2) | ((stop - start) << 8) | ((start & 0xffff) << 16);
 }
 
-struct SpecTask {
+struct __align__(8) SpecTask {
   int t0;       // starts[group start]
   unsigned pk;  // samples (8 bits) | K << 8 (6) | indels after the head << 14 (5) | (stop - start) << 19 (8)
   int start;    // group start (read base index)
   int lo;       // the group's first indel
+#if NRQ_SPEC_RETRY > 0
   int word0;    // spec_word(0, ...) of the group's first plan
   int nret;     // retries that led to this task
+#endif
 };
+// (without retry chains a task IS its group's first plan: 16 bytes instead of 24, and the 6 KB that saves in the
+// pool go to the slabs -- more lanes per batch)
+__device__ __forceinline__ int spec_task_word0(const SpecTask& tk) {
+#if NRQ_SPEC_RETRY > 0
+  return tk.word0;
+#else
+  return spec_word(0, (int)((tk.pk >> 8) & 63u), tk.start, tk.start + (int)((tk.pk >> 19) & 255u));
+#endif
+}
+__device__ __forceinline__ int spec_task_nret(const SpecTask& tk) {
+#if NRQ_SPEC_RETRY > 0
+  return tk.nret;
+#else
+  return 0;
+#endif
+}
 
 struct SpecSm {
   double lut[kSpecLut + 2];  // [kSpecLut] = +0.0: what a sample outside the region adds
   long long slab[kSpecWarps][kSpecSlab];
-  unsigned pick[kSpecWarps][8 * 32];  // bitmap of a lane's picks: word w of lane l at w * 32 + l
   SpecTask task[kSpecPool];
   unsigned short order[kSpecPool];
   int hist[256];
@@ -140,7 +157,10 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
                                                const int32_t* t, int last, int limit, int nt) {
   const bool act = lane < L;
   SpecTask tk;
-  tk.t0 = 0; tk.pk = 0u; tk.start = 0; tk.lo = 0; tk.word0 = 0; tk.nret = 0;
+  tk.t0 = 0; tk.pk = 0u; tk.start = 0; tk.lo = 0;
+#if NRQ_SPEC_RETRY > 0
+  tk.word0 = 0; tk.nret = 0;
+#endif
   if (act) tk = sm.task[sm.order[i0 + lane]];
   const int n = (int)(tk.pk & 255u);
   const int K = (int)((tk.pk >> 8) & 63u);
@@ -151,10 +171,13 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
   const int col = act ? lane : 0;
   long long* slab = sm.slab[warp];       // key i of this lane at slab[i * L + col], i < 8 nb_max
   int* bmaxh = reinterpret_cast<int*>(slab + nrd_max * L);  // largest high word of block b at bmaxh[b * L + col]
-  unsigned* pick = sm.pick[warp];
+  // bitmap of the lane's picks, one bit per running difference: word w at pick[w * L + col], behind the block maxima
+  // (a fixed 256 bits per lane took 8 KB of the CTA's shared memory, i.e. three to four lanes of every batch)
+  unsigned* pick = reinterpret_cast<unsigned*>(bmaxh + nb_max * L);
+  const int n_pw = (nb_max + 3) >> 2;
   __syncwarp();  // the previous batch's columns are laid out differently
-#pragma unroll
-  for (int w = 0; w < 8; ++w) pick[w * 32 + lane] = 0u;
+  if (act)
+    for (int w = 0; w < n_pw; ++w) pick[w * L + col] = 0u;
   if (act) {  // the tail of the lane's last block is never a candidate
     for (int j = nrd; j < 8 * nb_own; ++j) slab[j * L + col] = -1ll;
   }
@@ -260,7 +283,7 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
             if (kv >= best) { best = kv; bi = 8 * b + u; }
           }
         }
-        pick[(bi >> 5) * 32 + lane] |= 1u << (bi & 31);
+        pick[(bi >> 5) * L + col] |= 1u << (bi & 31);
 #pragma unroll
         for (int d = -kSpecM + 1; d <= kSpecM; ++d) {
           const int i = bi + d;
@@ -282,11 +305,11 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
     if (!fail) {
       const int base = atomicAdd(&sm.cpt_alloc, K);
       if (base + K <= min(cpt_cap, 1 << 24)) {
-        entry = make_int2(tk.word0 | kSpecFound, base | (tk.nret << 24));
+        entry = make_int2(spec_task_word0(tk) | kSpecFound, base | (spec_task_nret(tk) << 24));
         unsigned char* o = cpt_bytes + base;
         int c = 0;
         for (int w = 0; w * 32 < nrd; ++w) {
-          unsigned word = pick[w * 32 + lane];
+          unsigned word = pick[w * L + col];
           while (word) {
             const int bpos = __ffs(word) - 1;
             word &= word - 1;
@@ -295,7 +318,7 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
         }
       }
     } else {
-      bool again = tk.nret < kSpecMaxRetry && !(start == 0 && stop == last);
+      bool again = spec_task_nret(tk) < kSpecMaxRetry && !(start == 0 && stop == last);
       SpecTask nx = tk;
       if (again) {
         const int K2 = K + (start > 0) + (stop < last);
@@ -305,7 +328,9 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
         nx.t0 = ts;
         nx.pk = (unsigned)n2 | ((unsigned)K2 << 8) | (tk.pk & (31u << 14)) | ((unsigned)(e2 - s2) << 19);
         nx.start = s2;
+#if NRQ_SPEC_RETRY > 0
         nx.nret = tk.nret + 1;
+#endif
       }
       if (again) {
         const int slot = nt + atomicAdd(&sm.n_retry, 1);
@@ -313,7 +338,7 @@ __device__ __forceinline__ void spec_run_batch(SpecSm& sm, int warp, int lane, i
         if (again) sm.task[slot] = nx;
       }
       if (again) entry.x = -1;  // outcome still to come
-      else entry = make_int2(tk.word0 | kSpecNone, tk.nret << 24);  // nret + 1 searches without merges: all None
+      else entry = make_int2(spec_task_word0(tk) | kSpecNone, spec_task_nret(tk) << 24);  // nret + 1 searches without merges: all None
     }
     if (entry.x != -1) sp[tk.lo] = entry;
   }
@@ -429,9 +454,12 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
               const int u = __shfl_up_sync(kFull, pm, o);
               if (lane >= o) pm = max(pm, u);
             }
-            // per lane: 8 keys and half a key's worth of block maximum for every block of the largest region
+            // per lane: 8 keys and half a key's worth of block maximum for every block of the largest region, and a
+            // bit per key for the picks -- block maxima and pick words counted together in 4-byte units, rounded up
+            // to whole keys over the lanes taken
             const int nbp = (pm + 7) >> 3;
-            const bool fits = i0 + lane < nt && (lane + 1) * (8 * nbp + ((nbp + 1) >> 1)) <= kSpecSlab;
+            const int words = nbp + ((nbp + 3) >> 2);
+            const bool fits = i0 + lane < nt && (lane + 1) * 8 * nbp + (((lane + 1) * words + 1) >> 1) <= kSpecSlab;
             L = __popc(__ballot_sync(kFull, fits));  // a prefix of the lanes: the need only grows with the lane
             int won = 0;
             if (lane == 0) won = atomicCAS(&sm.cursor, i0, i0 + L) == i0;
@@ -533,8 +561,10 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
             tk.pk = (unsigned)n | ((unsigned)K << 8) | ((unsigned)(e - tid) << 14) | ((unsigned)(stop - start) << 19);
             tk.start = start;
             tk.lo = idx;
+#if NRQ_SPEC_RETRY > 0
             tk.word0 = spec_word(0, K, start, stop);
             tk.nret = 0;
+#endif
             sm.task[slot] = tk;
           }
         }
