@@ -33,7 +33,7 @@ namespace nrq {
 #define NRQ_SPEC_POOL 768
 #endif
 #ifndef NRQ_SPEC_SLAB
-#define NRQ_SPEC_SLAB 1376
+#define NRQ_SPEC_SLAB 1424
 #endif
 #ifndef NRQ_SPEC_MINB
 #define NRQ_SPEC_MINB 2
@@ -103,9 +103,9 @@ struct SpecSm {
   long long slab[kSpecWarps][kSpecSlab];
   SpecTask task[kSpecPool];
   unsigned short order[kSpecPool];
-  int hist[256];
-  int mi[kSpecThreads];  // running maximum of the indel ends, inclusive
-  int zs[kSpecThreads];  // sum of diffs up to and including this indel
+  // (the sort's histogram and the two planning arrays -- int hist[256], mi[kSpecThreads]: running maximum of the
+  // indel ends, inclusive, zs[kSpecThreads]: sum of diffs up to and including this indel -- live in the first
+  // warp's slab: planning, sort and search are separated by block barriers, and the 3 KB buy every warp 48 keys)
   unsigned heads[kSpecWarps];
   int wmax[kSpecWarps];
   int n_tasks, cursor, read, cpt_alloc, n_retry;
@@ -356,6 +356,10 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
   const int16_t* raw_lo = b.raw;
   const int16_t* raw_hi = b.raw + b.raw_off[b.n_reads];
   const int m = p.min_seg_len;
+  int* const hist_ = reinterpret_cast<int*>(sm.slab[0]);
+  int* const mi_ = hist_ + 256;
+  int* const zs_ = mi_ + kSpecThreads;
+  static_assert((256 + 2 * kSpecThreads) * sizeof(int) <= kSpecSlab * sizeof(long long), "planning arrays in a slab");
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -414,15 +418,15 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         // retry in the pool's tail, which is the pool of the next round
         int nt = nt_now;
         for (;;) {
-        for (int k = tid; k < 256; k += kSpecThreads) sm.hist[k] = 0;
+        for (int k = tid; k < 256; k += kSpecThreads) hist_[k] = 0;
         __syncthreads();
         for (int i = tid; i < nt; i += kSpecThreads)
-          atomicAdd(&sm.hist[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1);
+          atomicAdd(&hist_[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1);
         __syncthreads();
         if (warp == 0) {
           int v[8], s = 0;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { v[q] = sm.hist[8 * lane + q]; s += v[q]; }
+          for (int q = 0; q < 8; ++q) { v[q] = hist_[8 * lane + q]; s += v[q]; }
           int incl = s;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
@@ -431,11 +435,11 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
           }
           int run = incl - s;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { sm.hist[8 * lane + q] = run; run += v[q]; }
+          for (int q = 0; q < 8; ++q) { hist_[8 * lane + q] = run; run += v[q]; }
         }
         __syncthreads();
         for (int i = tid; i < nt; i += kSpecThreads)
-          sm.order[atomicAdd(&sm.hist[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1)] = (unsigned short)i;
+          sm.order[atomicAdd(&hist_[spec_bin(sm.task[i].pk, (sig_al + sm.task[i].t0) & 7)], 1)] = (unsigned short)i;
         if (tid == 0) { sm.cursor = 0; sm.n_retry = 0; }
         __syncthreads();
         for (;;) {
@@ -514,8 +518,8 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
       const bool brk = m_prev < my.x;  // no earlier indel reaches this one (:291-292)
       const unsigned hm = __ballot_sync(kFull, brk);
       if (lane == 0) sm.heads[warp] = hm;
-      sm.mi[tid] = M;
-      sm.zs[tid] = my.w + my.z;
+      mi_[tid] = M;
+      zs_[tid] = my.w + my.z;
       __syncthreads();
       int nh = -1;  // the next group's head inside the tile
       {
@@ -536,9 +540,9 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
       }
       if (brk && valid && nh >= 0) {  // extend_group (:203-216) for indels tid .. nh - 1
         const int e = nh - 1;
-        const int gmax = sm.mi[e];
+        const int gmax = mi_[e];
         int start = my.x, stop = gmax;
-        int K = (sm.zs[e] - my.w) + stop - start - 1;
+        int K = (zs_[e] - my.w) + stop - start - 1;
         bool ok = !(start < 0 || stop > last);
         int ts = 0, te = 0;
         while (ok) {
@@ -570,10 +574,10 @@ k_speculate(nrq_batch b, nrq_params p, const double* __restrict__ sv, const int6
         }
       }
       if (lh > 0) {
-        carry = sm.mi[lh - 1];
+        carry = mi_[lh - 1];
         tile += lh;
       } else {  // one group fills the tile (or the tile lies inside one): left to K2b
-        carry = sm.mi[kSpecThreads - 1];
+        carry = mi_[kSpecThreads - 1];
         tile += kSpecThreads;
       }
     }
