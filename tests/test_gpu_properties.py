@@ -227,3 +227,32 @@ def test_event_table_on_hand_made_segmentations(engine):
             a, b = fast[col][sl], exact[col][sl]
             assert not np.isnan(b).any()
             assert np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))) < tol, (r, kinds[r % len(kinds)], col)
+
+
+def test_long_reads_streamed_in_parts_give_the_same_table(engine):
+    """nrq_params.long_read_parts: a read of more than 262 144 samples is cut at base boundaries into parts, one
+    warp each (BASELINE configs[3]); a part is a read of its own from its first boundary on.  Same boundaries,
+    same start / length, same means bit for bit (every path uses one formula for a base without clipped samples),
+    standard deviations within a few ulps, and the whole table against the numpy-order kernel."""
+    from nanoraw_b200.engine import ResquiggleParams
+    genome = synth.make_genome(1_000_000, seed=23)
+    cfg = synth.SynthConfig(span_mean=36_000, span_sd=2_000, seed_base=65000)
+    reads = [synth.make_read(genome, synth.kmer_levels(cfg), cfg, i) for i in range(3)]
+    reads += [synth.make_read(genome, synth.kmer_levels(synth.SynthConfig(span_mean=3000, seed_base=65100)),
+                              synth.SynthConfig(span_mean=3000, seed_base=65100), 7)]  # a short one beside them
+    assert max(int(r.starts[-1]) for r in reads) > 262_144
+    batch = ReadBatch.from_reads(reads)
+    whole = engine.run(batch, ResquiggleParams(long_read_parts=1))
+    exact = engine.run(batch, ResquiggleParams(long_read_parts=1, exact_stats=True))
+    for parts in (2, 5, 16, 64):
+        cut = engine.run(batch, ResquiggleParams(long_read_parts=parts))
+        for r in range(len(reads)):
+            assert cut.ok(r) and whole.ok(r), (cut.error(r), whole.error(r))
+            assert np.array_equal(cut.new_segs_of(r), whole.new_segs_of(r))
+            a, b, c = cut.events_of(r), whole.events_of(r), exact.events_of(r)
+            for col in ('start', 'length', 'base'):
+                assert np.array_equal(a[col], b[col])
+            assert np.array_equal(a['norm_mean'], b['norm_mean'])
+            assert np.max(np.abs(a['norm_stdev'] - b['norm_stdev'])) < 1e-13
+            assert np.max(np.abs(a['norm_mean'] - c['norm_mean'])) < 1e-12
+            assert np.max(np.abs(a['norm_stdev'] - c['norm_stdev'])) < 1e-11
