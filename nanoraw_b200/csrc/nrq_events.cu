@@ -577,16 +577,18 @@ k_event_table(nrq_batch b, nrq_params p, const double* __restrict__ sv, const in
           const int n = pos - bpos;
           const int S1 = (int)(E1 - pE1);  // 0 <= S1 <= S2 < 2^32: d is a non-negative integer
           const unsigned S2 = E2 - pE2;
-          const double dn = (double)n;
+          // (an empty base -- never from nrq_resegment, whose reads have increasing boundaries -- divides by zero:
+          // 1 / 0 = inf, the Newton step makes it NaN, and NaN is what np.mean / np.std of nothing give)
+          const double dn = (double)max(n, 0);
           const double rn = ev_rcp(dn);
           // mean = (S1 / n + pivot - shift) / scale
-          double mean = fma((double)S1 * rn, R.inv_scale, R.c0), sd = qnan;
+          const double mean = fma((double)S1 * rn, R.inv_scale, R.c0);
+          double sd = qnan;
           if (R.compute_sd) {
             const unsigned long long num =
                 (unsigned long long)(unsigned)n * (unsigned long long)S2 - (unsigned long long)((long long)S1 * (long long)S1);
             sd = ev_sqrt_int((double)num) * (rn * R.inv_scale_abs);  // sqrt(num / n^2 / scale^2)
           }
-          if (n <= 0) { mean = qnan; sd = qnan; }
           const unsigned o = (unsigned)(cur + lane - 1);  // 32-bit index on per-read base pointers
           o_mean[o] = mean;
           o_sd[o] = sd;
