@@ -176,7 +176,9 @@ const char* nrq_status_message(int32_t st) {
     case NRQ_ST_UNSATISFIABLE:
       return "Indel region spans the whole read and still cannot be re-segmented (the reference does not "
              "terminate here).";
-    case NRQ_ST_REGION_TOO_LARGE: return "Indel region exceeds the re-squiggle workspace capacity.";
+    case NRQ_ST_REGION_TOO_LARGE:
+      // (not a reference message: the reference re-segments a region of any size, serially)
+      return "Indel region exceeds the re-squiggle workspace capacity (nrq_params.big_region_cap samples; the reference has no such limit).";
     case NRQ_ST_BAD_ALIGNMENT: return "Alignment does not start and end with matched bases.";
     case NRQ_ST_BAD_INPUT: return "Inconsistent or empty read data.";
     case NRQ_ST_WORKSPACE: return "Re-squiggle workspace too small for this read.";
